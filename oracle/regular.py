@@ -1,0 +1,105 @@
+"""Oracle restatement of the reference's NON-continual (clip) ST-GCN math, functional form.
+
+Test infrastructure only.  Operates directly on a state_dict in the regular ``StGcn`` key format
+(oracle/weights.py), eval mode (running BN statistics), torch CPU, dtype of the inputs (fp32 for
+parity, fp64 for the noise floor).
+
+Follows: models/base.py:260-270 (GraphConvolution.forward), :302-304 (TemporalConvolution.forward),
+:376-387 (SpatioTemporalBlock.forward), models/st_gcn/st_gcn.py:48-65 (StGcn.forward) and
+models/st_gcn_mod/st_gcn_mod.py:52-69 (StGcnMod.forward, identical body), models/base.py:73-101
+(CoModelBase clip-mode pipeline: data_bn, blocks, spatial mean, AvgPool1d, fc).
+"""
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # torch.nn.BatchNorm default, never overridden by the reference
+
+
+def _bn(x, sd, key):
+    w, b = sd[key + "weight"].to(x.dtype), sd[key + "bias"].to(x.dtype)
+    m, v = sd[key + "running_mean"].to(x.dtype), sd[key + "running_var"].to(x.dtype)
+    return F.batch_norm(x, m, v, w, b, training=False, eps=BN_EPS)
+
+
+def _conv(x, sd, key, stride=1, pad=0):
+    return F.conv2d(x, sd[key + "weight"].to(x.dtype), sd[key + "bias"].to(x.dtype), stride=(stride, 1), padding=(pad, 0))
+
+
+def graph_conv(x, sd, key):
+    """x (B, Cin, T, V) -> (B, Cout, T, V).  models/base.py:260-270."""
+    B, C, T, V = x.shape
+    adj = (sd[key + "A"] * sd[key + "graph_attn"]).to(x.dtype)
+    total = None
+    for part in range(3):
+        mixed = torch.matmul(x.reshape(B, C * T, V), adj[part]).reshape(B, C, T, V)
+        z = _conv(mixed, sd, key + f"g_conv.{part}.")
+        total = z if total is None else z + total
+    total = _bn(total, sd, key + "bn.")
+    if (key + "gcn_residual.0.weight") in sd:
+        skip = _bn(_conv(x, sd, key + "gcn_residual.0."), sd, key + "gcn_residual.1.")
+    else:
+        skip = x
+    return F.relu(total + skip)
+
+
+def temporal_conv(x, sd, key, stride, pad):
+    """models/base.py:291-304."""
+    return _bn(_conv(x, sd, key + "t_conv.", stride, pad), sd, key + "bn.")
+
+
+def st_block(x, sd, key, spec, pad):
+    """models/base.py:376-387; ``pad`` is temporal_padding (4 regular / 0 for the * variant)."""
+    z = temporal_conv(graph_conv(x, sd, key + "gcn."), sd, key + "tcn.", spec.stride, pad)
+    shrink = 4 - pad
+    xs = x[:, :, shrink: x.shape[2] - shrink] if shrink else x
+    if spec.res_kind == 0:
+        r = 0
+    elif spec.res_kind == 1:
+        r = xs
+    else:
+        r = temporal_conv(xs, sd, key + "residual.", spec.stride, 0)
+    return F.relu(z + r)
+
+
+def normalise_input(x, sd):
+    """(N, C, T, V, M) -> data_bn -> (N*M, C, T, V).  st_gcn.py:49-57 / base.py:73-82."""
+    N, C, T, V, M = x.shape
+    y = x.permute(0, 4, 3, 1, 2).contiguous().view(N, M * V * C, T)
+    y = _bn(y, sd, "data_bn.")
+    return y.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
+
+
+def stack_features(x, sd, arch, collect=None):
+    """Run all blocks on a clip (N*M, C, T, V); optionally collect per-block outputs."""
+    for name, spec in zip(arch.block_names, arch.blocks):
+        x = st_block(x, sd, name, spec, arch.padding)
+        if collect is not None:
+            collect.append(x)
+    return x
+
+
+def stgcn_forward(x, sd, arch, collect=None):
+    """Regular StGcn / StGcnMod clip forward -> (N, classes).  st_gcn.py:48-65."""
+    N, M = x.shape[0], x.shape[4]
+    y = stack_features(normalise_input(x, sd), sd, arch, collect)
+    c = y.shape[1]
+    y = y.view(N, M, c, -1).mean(3).mean(1)
+    return F.linear(y, sd["fc.weight"].to(y.dtype), sd["fc.bias"].to(y.dtype))
+
+
+def pooled_sequence(x, sd, arch):
+    """(N, C, T, V, M) -> spatially pooled last-block features (N, Cl, T_out).  base.py:84."""
+    N, M = x.shape[0], x.shape[4]
+    y = stack_features(normalise_input(x, sd), sd, arch)
+    _, c, t, v = y.shape
+    return y.view(N, M, c, t, v).mean(4).mean(1)
+
+
+def co_clip_forward(x, sd, arch):
+    """What CoStGcn/CoStGcnMod ``forward`` returns in clip mode: AvgPool1d(pool_size, 1,
+    pool_padding) over the pooled sequence, fc per time step, first step kept
+    (models/base.py:97-101,166-181)."""
+    h = pooled_sequence(x, sd, arch)
+    h = F.avg_pool1d(h, arch.pool_size, stride=1, padding=arch.pool_padding)  # count_include_pad
+    logits = torch.einsum("kc,nct->nkt", sd["fc.weight"].to(h.dtype), h) + sd["fc.bias"].to(h.dtype)[None, :, None]
+    return logits[:, :, 0]
