@@ -1,0 +1,816 @@
+// libcosk: C ABI + host-side step orchestration for the continual ST-GCN forward on sm_100a.
+// See include/cosk.h for the contract and DESIGN.md for the data layout.
+#include "../../include/cosk.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+
+using namespace cosk;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct ActBuf {  // token-major split-bf16 activation ring: [slots][plane hi/lo][t_alloc][cs]
+  __nv_bfloat16 *ptr = nullptr;
+  int slots = 0, cs = 0, c = 0;
+  long long t_alloc = 0;
+  bool has_map = false;
+  CUtensorMap map;
+  size_t bytes() const { return (size_t)slots * 2 * t_alloc * cs * sizeof(__nv_bfloat16); }
+  __nv_bfloat16 *hi(int slot) const { return ptr + (size_t)slot * 2 * t_alloc * cs; }
+  __nv_bfloat16 *lo(int slot) const { return hi(slot) + (size_t)t_alloc * cs; }
+  long long row_hi(int slot) const { return (long long)slot * 2 * t_alloc; }
+};
+
+struct BlockW {
+  // host copies as loaded (BN already folded by the caller)
+  std::vector<float> mix, gcn_w, gcn_b, tcn_w, res_w, tcn_b;
+  // device, SIMT format (k-major fp32)
+  float *d_gcn_w = nullptr, *d_gcn_b = nullptr, *d_tcn_w = nullptr, *d_res_w = nullptr, *d_tcn_b = nullptr;
+  int *d_mix_ptr = nullptr, *d_mix_src = nullptr;
+  float *d_mix_val = nullptr;
+  int mix_max_nz = 0;
+  // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
+  __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
+  CUtensorMap map_gcn_w, map_tcn_w;
+  bool tc_gcn = false, tc_tcn = false;
+  long long n_in = 0, n_out = 0;
+  ActBuf ring, out;
+};
+
+struct ProfRec {
+  int kind, block;
+  cudaEvent_t ev;
+};
+
+}  // namespace
+
+struct cosk_model {
+  cosk_config cfg;
+  int num_sms = 148;
+  EncodeTiledFn encode = nullptr;
+  std::vector<BlockW> blk;
+  std::vector<float> h_bn_scale, h_bn_shift, h_fc_w, h_fc_b;
+  float *d_bn_scale = nullptr, *d_bn_shift = nullptr, *d_fc_w = nullptr, *d_fc_b = nullptr;
+  bool prepared = false;
+  // state
+  long long n_streams = 0, n_tokens = 0, t_alloc = 0;
+  int skel_per_tile = 0, tile_tokens = 0, n_tiles = 0;
+  ActBuf xin;
+  float *d_pool_ring = nullptr;
+  double *d_pool_sum = nullptr;
+  long long pool_n = 0, frame = 0;
+  std::vector<int32_t> last_flags;
+  unsigned int *d_dbg = nullptr;
+  int64_t launches = 0;
+  int64_t state_bytes = 0;
+  // profiling
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(cosk_model *m, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (m) m->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(m, COSK_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_state(cosk_model *m) {
+  dfree(m->xin.ptr);
+  for (auto &b : m->blk) {
+    dfree(b.ring.ptr);
+    dfree(b.out.ptr);
+  }
+  dfree(m->d_pool_ring);
+  dfree(m->d_pool_sum);
+  m->n_streams = 0;
+  m->state_bytes = 0;
+}
+
+int make_map(cosk_model *m, CUtensorMap *map, void *base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(m, COSK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) cols=%llu rows=%llu", (int)r,
+                                     (unsigned long long)cols, (unsigned long long)rows);
+  return COSK_OK;
+}
+
+int alloc_act(cosk_model *m, ActBuf &b, int slots, int c) {
+  b.slots = slots;
+  b.c = c;
+  b.cs = round_up(c, 8);
+  b.t_alloc = m->t_alloc;
+  CK(cudaMalloc(&b.ptr, b.bytes()));
+  m->state_bytes += (int64_t)b.bytes();
+  b.has_map = false;
+  if (b.cs % kBK == 0) {
+    int rc = make_map(m, &b.map, b.ptr, (uint64_t)b.cs, (uint64_t)slots * 2 * b.t_alloc, kTileRows);
+    if (rc) return rc;
+    b.has_map = true;
+  }
+  return COSK_OK;
+}
+
+template <typename T>
+int upload(cosk_model *m, T *&dst, const T *src, size_t n) {
+  dfree(dst);
+  CK(cudaMalloc(&dst, n * sizeof(T)));
+  CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return COSK_OK;
+}
+
+// [rows][K] fp32 (K contiguous) -> k-major [K][rows]
+std::vector<float> transpose(const float *w, int rows, int K) {
+  std::vector<float> t((size_t)rows * K);
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < K; ++k) t[(size_t)k * rows + r] = w[(size_t)r * K + k];
+  return t;
+}
+
+inline uint16_t f2bf(float x) {  // round-to-nearest-even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// [rows][K] fp32 -> [2*rows][K] bf16: hi rows then lo rows
+std::vector<uint16_t> split_rows(const std::vector<float> &w, int rows, int K) {
+  std::vector<uint16_t> o((size_t)2 * rows * K);
+  for (size_t i = 0; i < (size_t)rows * K; ++i) {
+    uint16_t h = f2bf(w[i]);
+    o[i] = h;
+    o[(size_t)rows * K + i] = f2bf(w[i] - bf2f(h));
+  }
+  return o;
+}
+
+bool tc_width(int c) { return c == 64 || c == 128 || c == 256; }
+
+int prepare(cosk_model *m) {
+  const cosk_config &c = m->cfg;
+  const int V = c.vertices;
+  if (c.data_bn) {
+    size_t n = (size_t)c.persons * V * c.c_in;
+    if (m->h_bn_scale.size() != n || m->h_bn_shift.size() != n) return fail(m, COSK_ERR_STATE, "data_bn weights missing");
+    int rc = upload(m, m->d_bn_scale, m->h_bn_scale.data(), n);
+    if (rc) return rc;
+    rc = upload(m, m->d_bn_shift, m->h_bn_shift.data(), n);
+    if (rc) return rc;
+  }
+  if (c.classes > 0) {
+    size_t n = (size_t)c.classes * c.blocks[c.n_blocks - 1].cout;
+    if (m->h_fc_w.size() != n || m->h_fc_b.size() != (size_t)c.classes) return fail(m, COSK_ERR_STATE, "fc weights missing");
+    int rc = upload(m, m->d_fc_w, m->h_fc_w.data(), n);
+    if (rc) return rc;
+    rc = upload(m, m->d_fc_b, m->h_fc_b.data(), (size_t)c.classes);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < c.n_blocks; ++i) {
+    const cosk_block_cfg &bc = c.blocks[i];
+    BlockW &b = m->blk[i];
+    const int res_conv = bc.cin != bc.cout ? 1 : 0;
+    const int Kg = (3 + res_conv) * bc.cin, Kt = kTaps * bc.cout;
+    if (b.mix.size() != (size_t)3 * V * V) return fail(m, COSK_ERR_STATE, "block%d.mix missing", i);
+    if (b.gcn_w.size() != (size_t)bc.cout * Kg) return fail(m, COSK_ERR_STATE, "block%d.gcn.w missing or wrong size", i);
+    if (b.gcn_b.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.gcn.b missing", i);
+    if (b.tcn_w.size() != (size_t)bc.cout * Kt) return fail(m, COSK_ERR_STATE, "block%d.tcn.w missing", i);
+    if (b.tcn_b.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.tcn.b missing", i);
+    if (bc.res_kind == COSK_RES_CONV && b.res_w.size() != (size_t)bc.cout * bc.cin)
+      return fail(m, COSK_ERR_STATE, "block%d.res.w missing", i);
+    // CSR of A * graph_attn over (partition, output vertex)
+    std::vector<int> ptr(3 * V + 1, 0), src;
+    std::vector<float> val;
+    b.mix_max_nz = 0;
+    for (int p = 0; p < 3; ++p)
+      for (int w = 0; w < V; ++w) {
+        int cnt = 0;
+        for (int v = 0; v < V; ++v) {
+          float a = b.mix[((size_t)p * V + v) * V + w];
+          if (a != 0.f) {
+            src.push_back(v);
+            val.push_back(a);
+            ++cnt;
+          }
+        }
+        ptr[p * V + w + 1] = (int)src.size();
+        if (cnt > b.mix_max_nz) b.mix_max_nz = cnt;
+      }
+    if (src.empty()) {
+      src.push_back(0);
+      val.push_back(0.f);
+    }
+    int rc;
+    if ((rc = upload(m, b.d_mix_ptr, ptr.data(), ptr.size()))) return rc;
+    if ((rc = upload(m, b.d_mix_src, src.data(), src.size()))) return rc;
+    if ((rc = upload(m, b.d_mix_val, val.data(), val.size()))) return rc;
+    // SIMT weights
+    std::vector<float> t = transpose(b.gcn_w.data(), bc.cout, Kg);
+    if ((rc = upload(m, b.d_gcn_w, t.data(), t.size()))) return rc;
+    if ((rc = upload(m, b.d_gcn_b, b.gcn_b.data(), b.gcn_b.size()))) return rc;
+    t = transpose(b.tcn_w.data(), bc.cout, Kt);
+    if ((rc = upload(m, b.d_tcn_w, t.data(), t.size()))) return rc;
+    if ((rc = upload(m, b.d_tcn_b, b.tcn_b.data(), b.tcn_b.size()))) return rc;
+    if (bc.res_kind == COSK_RES_CONV) {
+      t = transpose(b.res_w.data(), bc.cout, bc.cin);
+      if ((rc = upload(m, b.d_res_w, t.data(), t.size()))) return rc;
+    }
+    // tensor-core eligibility + weights
+    const bool want_tc = c.path == COSK_PATH_AUTO;
+    b.tc_gcn = want_tc && tc_width(bc.cout) && bc.cin % kBK == 0 && b.mix_max_nz <= kMixMaxNz;
+    b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
+    if (b.tc_gcn) {
+      std::vector<uint16_t> s = split_rows(b.gcn_w, bc.cout, Kg);
+      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
+      if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)Kg, (uint64_t)2 * bc.cout, (uint32_t)bc.cout))) return rc;
+    }
+    if (b.tc_tcn) {
+      const int Kr = bc.res_kind == COSK_RES_CONV ? bc.cin : 0;
+      std::vector<float> cat((size_t)bc.cout * (Kt + Kr));
+      for (int r = 0; r < bc.cout; ++r) {
+        memcpy(&cat[(size_t)r * (Kt + Kr)], &b.tcn_w[(size_t)r * Kt], sizeof(float) * Kt);
+        if (Kr) memcpy(&cat[(size_t)r * (Kt + Kr) + Kt], &b.res_w[(size_t)r * Kr], sizeof(float) * Kr);
+      }
+      std::vector<uint16_t> s = split_rows(cat, bc.cout, Kt + Kr);
+      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_tcn_w16), s.data(), s.size()))) return rc;
+      if ((rc = make_map(m, &b.map_tcn_w, b.d_tcn_w16, (uint64_t)(Kt + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout)))
+        return rc;
+    }
+  }
+  m->prepared = true;
+  return COSK_OK;
+}
+
+int zero_state(cosk_model *m, cudaStream_t s) {
+  CK(cudaMemsetAsync(m->xin.ptr, 0, m->xin.bytes(), s));
+  for (auto &b : m->blk) {
+    CK(cudaMemsetAsync(b.ring.ptr, 0, b.ring.bytes(), s));
+    CK(cudaMemsetAsync(b.out.ptr, 0, b.out.bytes(), s));
+    b.n_in = b.n_out = 0;
+  }
+  if (m->cfg.classes > 0) {
+    const size_t cl = (size_t)m->cfg.blocks[m->cfg.n_blocks - 1].cout;
+    CK(cudaMemsetAsync(m->d_pool_ring, 0, (size_t)m->cfg.pool_size * m->n_streams * cl * sizeof(float), s));
+    CK(cudaMemsetAsync(m->d_pool_sum, 0, (size_t)m->n_streams * cl * sizeof(double), s));
+  }
+  CK(cudaMemsetAsync(m->d_dbg, 0, 4 * sizeof(unsigned int), s));
+  m->pool_n = 0;
+  m->frame = 0;
+  std::fill(m->last_flags.begin(), m->last_flags.end(), 0);
+  return COSK_OK;
+}
+
+int prof_mark(cosk_model *m, int kind, int block, cudaStream_t s) {
+  if (!m->prof_on) return COSK_OK;
+  if (m->ev_used == m->ev_pool.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    m->ev_pool.push_back(e);
+  }
+  cudaEvent_t e = m->ev_pool[m->ev_used++];
+  CK(cudaEventRecord(e, s));
+  m->prof.push_back({kind, block, e});
+  return COSK_OK;
+}
+
+template <int COUT>
+int launch_tc_tcn(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  k_tc_tcn<COUT><<<grid, 256, TcTcnCfg<COUT>::kSmemBytes, s>>>(args);
+  CK(cudaGetLastError());
+  return COSK_OK;
+}
+template <int COUT>
+int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  k_tc_gcn<COUT><<<grid, 384, TcGcnCfg<COUT>::kSmemBytes, s>>>(args);
+  CK(cudaGetLastError());
+  return COSK_OK;
+}
+
+int set_smem_attrs(cosk_model *m) {
+  CK(cudaFuncSetAttribute(k_tc_tcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<64>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<128>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<256>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<64>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<128>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<256>::kSmemBytes));
+  return COSK_OK;
+}
+
+int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, cudaStream_t s) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  const int res_conv = bc.cin != bc.cout ? 1 : 0;
+  int rc = prof_mark(m, 1, i, s);
+  if (rc) return rc;
+  if (b.tc_gcn) {
+    TcGcnArgs a;
+    a.tm_x = in.map;
+    a.tm_w = b.map_gcn_w;
+    a.x_row = (int)in.row_hi(in_slot);
+    a.t_alloc = (int)m->t_alloc;
+    a.cin = bc.cin;
+    a.res_conv = res_conv;
+    a.V = m->cfg.vertices;
+    a.n_tiles = m->n_tiles;
+    a.tile_tokens = m->tile_tokens;
+    a.n_tokens = m->n_tokens;
+    a.mix_ptr = b.d_mix_ptr;
+    a.mix_src = b.d_mix_src;
+    a.mix_val = b.d_mix_val;
+    a.epi.bias = b.d_gcn_b;
+    a.epi.r_hi = res_conv ? nullptr : in.hi(in_slot);
+    a.epi.r_lo = res_conv ? nullptr : in.lo(in_slot);
+    a.epi.cs_r = in.cs;
+    a.epi.y_hi = b.ring.hi(ring_slot);
+    a.epi.y_lo = b.ring.lo(ring_slot);
+    a.epi.cs_out = b.ring.cs;
+    a.dbg = m->d_dbg;
+    if (bc.cout == 64) rc = launch_tc_gcn<64>(m, a, s);
+    else if (bc.cout == 128) rc = launch_tc_gcn<128>(m, a, s);
+    else rc = launch_tc_gcn<256>(m, a, s);
+    if (rc) return rc;
+  } else {
+    GcnArgs a;
+    a.x_hi = in.hi(in_slot);
+    a.x_lo = in.lo(in_slot);
+    a.cs_in = in.cs;
+    a.cin = bc.cin;
+    a.y_hi = b.ring.hi(ring_slot);
+    a.y_lo = b.ring.lo(ring_slot);
+    a.cs_out = b.ring.cs;
+    a.cout = bc.cout;
+    a.w = b.d_gcn_w;
+    a.bias = b.d_gcn_b;
+    a.res_conv = res_conv;
+    a.res_identity = !res_conv;
+    a.mix_ptr = b.d_mix_ptr;
+    a.mix_src = b.d_mix_src;
+    a.mix_val = b.d_mix_val;
+    a.V = m->cfg.vertices;
+    a.n_tokens = m->n_tokens;
+    a.tile_tokens = m->tile_tokens;
+    dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
+    k_gcn_simt<<<grid, 256, 0, s>>>(a);
+    CK(cudaGetLastError());
+  }
+  m->launches++;
+  return COSK_OK;
+}
+
+int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, int out_slot, cudaStream_t s) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  int rc = prof_mark(m, 2, i, s);
+  if (rc) return rc;
+  int tap_slot[kTaps];
+  for (int k = 0; k < kTaps; ++k) tap_slot[k] = (int)((n + 1 + k) % kRingSlots);  // frame n-8+k
+  if (b.tc_tcn) {
+    TcTcnArgs a;
+    a.tm_ring = b.ring.map;
+    a.tm_res = bc.res_kind == COSK_RES_CONV ? in.map : b.ring.map;
+    a.tm_w = b.map_tcn_w;
+    for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi(tap_slot[k]);
+    a.res_row = (int)in.row_hi(res_slot);
+    a.t_alloc = (int)m->t_alloc;
+    a.kb_per_tap = bc.cout / kBK;
+    a.kb_res = bc.res_kind == COSK_RES_CONV ? bc.cin / kBK : 0;
+    a.n_tiles = m->n_tiles;
+    a.tile_tokens = m->tile_tokens;
+    a.n_tokens = m->n_tokens;
+    a.epi.bias = b.d_tcn_b;
+    a.epi.r_hi = bc.res_kind == COSK_RES_IDENTITY ? in.hi(res_slot) : nullptr;
+    a.epi.r_lo = bc.res_kind == COSK_RES_IDENTITY ? in.lo(res_slot) : nullptr;
+    a.epi.cs_r = in.cs;
+    a.epi.y_hi = b.out.hi(out_slot);
+    a.epi.y_lo = b.out.lo(out_slot);
+    a.epi.cs_out = b.out.cs;
+    a.dbg = m->d_dbg;
+    if (bc.cout == 64) rc = launch_tc_tcn<64>(m, a, s);
+    else if (bc.cout == 128) rc = launch_tc_tcn<128>(m, a, s);
+    else rc = launch_tc_tcn<256>(m, a, s);
+    if (rc) return rc;
+  } else {
+    TcnArgs a;
+    for (int k = 0; k < kTaps; ++k) {
+      a.tap_hi[k] = b.ring.hi(tap_slot[k]);
+      a.tap_lo[k] = b.ring.lo(tap_slot[k]);
+    }
+    a.cs = b.ring.cs;
+    a.c = bc.cout;
+    a.w = b.d_tcn_w;
+    a.r_hi = in.hi(res_slot);
+    a.r_lo = in.lo(res_slot);
+    a.cs_r = in.cs;
+    a.cr = bc.cin;
+    a.res_kind = bc.res_kind;
+    a.w_r = b.d_res_w;
+    a.bias = b.d_tcn_b;
+    a.y_hi = b.out.hi(out_slot);
+    a.y_lo = b.out.lo(out_slot);
+    a.cs_out = b.out.cs;
+    a.n_tokens = m->n_tokens;
+    a.tile_tokens = m->tile_tokens;
+    dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
+    k_tcn_simt<<<grid, 256, 0, s>>>(a);
+    CK(cudaGetLastError());
+  }
+  m->launches++;
+  return COSK_OK;
+}
+
+int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s) {
+  const cosk_config &c = m->cfg;
+  int rc;
+  // input frame -> token rows (data_bn folded in)
+  const int xslot = (int)(m->frame % kOutSlots);
+  if ((rc = prof_mark(m, 0, -1, s))) return rc;
+  {
+    const long long total = m->n_tokens * m->xin.cs;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    k_input<<<(unsigned)blocks, threads, 0, s>>>(x, nc_stride, c.c_in, c.vertices, c.persons,
+                                                c.data_bn ? m->d_bn_scale : nullptr, c.data_bn ? m->d_bn_shift : nullptr,
+                                                m->xin.hi(xslot), m->xin.lo(xslot), m->xin.cs, m->n_tokens);
+    CK(cudaGetLastError());
+    m->launches++;
+  }
+  const ActBuf *in = &m->xin;
+  bool alive = true;
+  const int first = (kTaps - 1) - c.padding;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    m->last_flags[i] = 0;
+    if (!alive) continue;
+    BlockW &b = m->blk[i];
+    const cosk_block_cfg &bc = c.blocks[i];
+    const long long n = b.n_in;  // index of this input == index of the predecessor's emission
+    const int in_slot = (int)(n % kOutSlots);
+    if ((rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) return rc;
+    const bool fire = n >= first && (n - first) % bc.stride == 0;
+    if (fire) {
+      const int res_slot = (int)((n - kResDelay) % kOutSlots);  // n >= first >= 4
+      if ((rc = run_tcn(m, i, *in, res_slot, n, (int)(b.n_out % kOutSlots), s))) return rc;
+      b.n_out++;
+    }
+    b.n_in++;
+    alive = fire;
+    m->last_flags[i] = fire ? 1 : 0;
+    in = &b.out;
+  }
+  int emit = 0;
+  if (alive) {
+    const BlockW &last = m->blk[c.n_blocks - 1];
+    const int slot = (int)((last.n_out - 1) % kOutSlots);
+    if (c.classes > 0) {
+      emit = m->pool_n >= (long long)c.pool_size - 1 - c.pool_padding ? 1 : 0;
+      if ((rc = prof_mark(m, 3, -1, s))) return rc;
+      HeadArgs h;
+      h.y_hi = last.out.hi(slot);
+      h.y_lo = last.out.lo(slot);
+      h.cs = last.out.cs;
+      h.c = last.out.c;
+      h.V = c.vertices;
+      h.S = c.persons;
+      h.ring = m->d_pool_ring;
+      h.sum = m->d_pool_sum;
+      h.slot = (int)(m->pool_n % c.pool_size);
+      h.P = c.pool_size;
+      h.n_streams = m->n_streams;
+      h.emit = emit;
+      h.w = m->d_fc_w;
+      h.b = m->d_fc_b;
+      h.classes = c.classes;
+      h.out = out;
+      k_head<<<(unsigned)m->n_streams, 256, last.out.c * sizeof(float), s>>>(h);
+      CK(cudaGetLastError());
+      m->launches++;
+      m->pool_n++;
+    } else {
+      emit = 1;
+      const long long total = m->n_tokens * last.out.c;
+      k_read_block<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(last.out.hi(slot), last.out.lo(slot), last.out.cs,
+                                                                  last.out.c, c.vertices, m->n_tokens, out);
+      CK(cudaGetLastError());
+      m->launches++;
+    }
+  }
+  if ((rc = prof_mark(m, -1, -1, s))) return rc;  // closes the last interval of this step
+  m->last_flags[c.n_blocks] = emit;
+  m->frame++;
+  if (emitted) *emitted = emit;
+  return COSK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cosk_version(void) { return "cosk 0.1 (sm_100a)"; }
+
+const char *cosk_last_error(const cosk_model *m) { return m ? m->err.c_str() : "null handle"; }
+
+int cosk_create(const cosk_config *cfg, cosk_model **out) {
+  if (!cfg || !out) return COSK_ERR_ARG;
+  *out = nullptr;
+  if (cfg->abi_version != COSK_ABI_VERSION) return COSK_ERR_ARG;
+  if (cfg->n_blocks < 1 || cfg->n_blocks > COSK_MAX_BLOCKS) return COSK_ERR_ARG;
+  if (cfg->vertices < 1 || cfg->vertices > kTileRows || cfg->persons < 1 || cfg->c_in < 1) return COSK_ERR_ARG;
+  if (cfg->padding != 0 && cfg->padding != 4) return COSK_ERR_ARG;
+  if (cfg->classes > 0 && (cfg->pool_size < 1 || cfg->pool_padding < 0 || cfg->pool_padding >= cfg->pool_size))
+    return COSK_ERR_ARG;
+  int prev = cfg->c_in;
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const cosk_block_cfg &b = cfg->blocks[i];
+    if (b.cin != prev || b.cout < 1 || (b.stride != 1 && b.stride != 2)) return COSK_ERR_ARG;
+    if (b.res_kind == COSK_RES_IDENTITY && (b.cin != b.cout || b.stride != 1)) return COSK_ERR_ARG;
+    if (b.res_kind < 0 || b.res_kind > 2) return COSK_ERR_ARG;
+    prev = b.cout;
+  }
+  cosk_model *m = new cosk_model();
+  m->cfg = *cfg;
+  m->blk.resize(cfg->n_blocks);
+  m->last_flags.assign(cfg->n_blocks + 1, 0);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+    delete m;
+    return COSK_ERR_CUDA;  // no CPU fallback: the library is useless without a CUDA device
+  }
+  cudaSetDevice(cfg->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  m->num_sms = prop.multiProcessorCount;
+  const bool sm100 = prop.major == 10;
+  if (!sm100 && cfg->path == COSK_PATH_AUTO) {
+    delete m;
+    return COSK_ERR_UNSUPPORTED;  // the tcgen05 kernels are sm_100a only
+  }
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr) {
+    delete m;
+    return COSK_ERR_CUDA;
+  }
+  m->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaMalloc(&m->d_dbg, 4 * sizeof(unsigned int)) != cudaSuccess) {
+    delete m;
+    return COSK_ERR_CUDA;
+  }
+  cudaMemset(m->d_dbg, 0, 4 * sizeof(unsigned int));
+  if (sm100 && set_smem_attrs(m) != COSK_OK) {
+    fprintf(stderr, "cosk_create: %s\n", m->err.c_str());
+    cudaFree(m->d_dbg);
+    delete m;
+    return COSK_ERR_CUDA;
+  }
+  *out = m;
+  return COSK_OK;
+}
+
+void cosk_destroy(cosk_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  free_state(m);
+  for (auto &b : m->blk) {
+    dfree(b.d_gcn_w);
+    dfree(b.d_gcn_b);
+    dfree(b.d_tcn_w);
+    dfree(b.d_res_w);
+    dfree(b.d_tcn_b);
+    dfree(b.d_mix_ptr);
+    dfree(b.d_mix_src);
+    dfree(b.d_mix_val);
+    dfree(b.d_gcn_w16);
+    dfree(b.d_tcn_w16);
+  }
+  dfree(m->d_bn_scale);
+  dfree(m->d_bn_shift);
+  dfree(m->d_fc_w);
+  dfree(m->d_fc_b);
+  dfree(m->d_dbg);
+  for (auto e : m->ev_pool) cudaEventDestroy(e);
+  delete m;
+}
+
+int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t n) {
+  if (!m || !name || !host) return COSK_ERR_ARG;
+  std::vector<float> v(host, host + n);
+  std::string s(name);
+  m->prepared = false;
+  if (s == "data_bn.scale") m->h_bn_scale = v;
+  else if (s == "data_bn.shift") m->h_bn_shift = v;
+  else if (s == "fc.w") m->h_fc_w = v;
+  else if (s == "fc.b") m->h_fc_b = v;
+  else if (s.rfind("block", 0) == 0) {
+    size_t dot = s.find('.');
+    if (dot == std::string::npos) return fail(m, COSK_ERR_ARG, "bad tensor name %s", name);
+    int i = atoi(s.substr(5, dot - 5).c_str());
+    if (i < 0 || i >= m->cfg.n_blocks) return fail(m, COSK_ERR_ARG, "bad block index in %s", name);
+    std::string f = s.substr(dot + 1);
+    BlockW &b = m->blk[i];
+    if (f == "mix") b.mix = v;
+    else if (f == "gcn.w") b.gcn_w = v;
+    else if (f == "gcn.b") b.gcn_b = v;
+    else if (f == "tcn.w") b.tcn_w = v;
+    else if (f == "res.w") b.res_w = v;
+    else if (f == "tcn.b") b.tcn_b = v;
+    else return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
+  } else {
+    return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
+  }
+  return COSK_OK;
+}
+
+int cosk_set_batch(cosk_model *m, int64_t n_streams) {
+  if (!m || n_streams < 1) return COSK_ERR_ARG;
+  cudaSetDevice(m->cfg.device);
+  if (!m->prepared) {
+    int rc = prepare(m);
+    if (rc) return rc;
+  }
+  CK(cudaDeviceSynchronize());
+  free_state(m);
+  const cosk_config &c = m->cfg;
+  m->n_streams = n_streams;
+  const long long skel = n_streams * c.persons;
+  m->n_tokens = skel * c.vertices;
+  m->skel_per_tile = kTileRows / c.vertices;
+  m->tile_tokens = m->skel_per_tile * c.vertices;
+  m->n_tiles = (int)((skel + m->skel_per_tile - 1) / m->skel_per_tile);
+  m->t_alloc = round_up((int)((long long)m->n_tiles * m->tile_tokens + (kTileRows - m->tile_tokens)), 8);
+  if ((long long)kRingSlots * 2 * m->t_alloc > 0x7fffffffLL) return fail(m, COSK_ERR_ARG, "too many streams for 32-bit rows");
+  int rc = alloc_act(m, m->xin, kOutSlots, c.c_in);
+  if (rc) return rc;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    if ((rc = alloc_act(m, m->blk[i].ring, kRingSlots, c.blocks[i].cout))) return rc;
+    if ((rc = alloc_act(m, m->blk[i].out, kOutSlots, c.blocks[i].cout))) return rc;
+  }
+  if (c.classes > 0) {
+    const size_t cl = (size_t)c.blocks[c.n_blocks - 1].cout;
+    CK(cudaMalloc(&m->d_pool_ring, (size_t)c.pool_size * n_streams * cl * sizeof(float)));
+    CK(cudaMalloc(&m->d_pool_sum, (size_t)n_streams * cl * sizeof(double)));
+    m->state_bytes += (int64_t)((size_t)c.pool_size * n_streams * cl * sizeof(float) + (size_t)n_streams * cl * sizeof(double));
+  }
+  rc = zero_state(m, 0);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  return COSK_OK;
+}
+
+int cosk_reset(cosk_model *m) {
+  if (!m) return COSK_ERR_ARG;
+  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_reset before cosk_set_batch");
+  cudaSetDevice(m->cfg.device);
+  CK(cudaDeviceSynchronize());
+  int rc = zero_state(m, 0);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  return COSK_OK;
+}
+
+int cosk_step(cosk_model *m, const float *x_dev, int64_t nc_stride, float *out_dev, int32_t *emitted, void *stream) {
+  if (!m || !x_dev || !out_dev) return COSK_ERR_ARG;
+  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_step before cosk_set_batch");
+  cudaSetDevice(m->cfg.device);
+  return step_impl(m, x_dev, nc_stride, out_dev, emitted, (cudaStream_t)stream);
+}
+
+int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride, int32_t max_out,
+               int32_t *n_emitted, void *stream) {
+  if (!m || !x_dev || !out_dev || T < 0) return COSK_ERR_ARG;
+  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_steps before cosk_set_batch");
+  cudaSetDevice(m->cfg.device);
+  const long long frame_elems = (long long)m->cfg.vertices * m->cfg.persons;
+  int32_t cnt = 0;
+  for (int t = 0; t < T; ++t) {
+    int32_t em = 0;
+    // once max_out emissions are stored, later ones land in the last slot
+    const int32_t dst = cnt < max_out ? cnt : max_out - 1;
+    int rc = step_impl(m, x_dev + t * frame_elems, (long long)T * frame_elems, out_dev + (long long)dst * out_stride, &em,
+                       (cudaStream_t)stream);
+    if (rc) return rc;
+    cnt += em;
+  }
+  if (n_emitted) *n_emitted = cnt;
+  return COSK_OK;
+}
+
+int64_t cosk_state_bytes(const cosk_model *m) { return m ? m->state_bytes : 0; }
+
+int cosk_last_schedule(const cosk_model *m, int32_t *flags, int32_t n) {
+  if (!m || !flags || n < m->cfg.n_blocks + 1) return COSK_ERR_ARG;
+  for (int i = 0; i <= m->cfg.n_blocks; ++i) flags[i] = m->last_flags[i];
+  return COSK_OK;
+}
+
+int64_t cosk_frame_count(const cosk_model *m) { return m ? m->frame : 0; }
+
+int cosk_read_block(cosk_model *m, int32_t block, float *dst_dev, void *stream) {
+  if (!m || !dst_dev || block < 0 || block >= m->cfg.n_blocks) return COSK_ERR_ARG;
+  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_read_block before cosk_set_batch");
+  const BlockW &b = m->blk[block];
+  if (b.n_out == 0) return fail(m, COSK_ERR_STATE, "block %d has not emitted yet", block);
+  cudaSetDevice(m->cfg.device);
+  const int slot = (int)((b.n_out - 1) % kOutSlots);
+  const long long total = m->n_tokens * b.out.c;
+  k_read_block<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(b.out.hi(slot), b.out.lo(slot), b.out.cs,
+                                                                                 b.out.c, m->cfg.vertices, m->n_tokens, dst_dev);
+  CK(cudaGetLastError());
+  m->launches++;
+  return COSK_OK;
+}
+
+int64_t cosk_launch_count(const cosk_model *m) { return m ? m->launches : 0; }
+
+int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block) {
+  if (!m || block < 0 || block >= m->cfg.n_blocks) return COSK_ERR_ARG;
+  return (m->blk[block].tc_gcn ? 1 : 0) | (m->blk[block].tc_tcn ? 2 : 0);
+}
+
+int cosk_device_error(cosk_model *m, uint32_t *code) {
+  if (!m || !code) return COSK_ERR_ARG;
+  cudaSetDevice(m->cfg.device);
+  unsigned int h[4] = {0, 0, 0, 0};
+  CK(cudaMemcpy(h, m->d_dbg, sizeof h, cudaMemcpyDeviceToHost));
+  *code = h[0];
+  return COSK_OK;
+}
+
+int cosk_profile_enable(cosk_model *m, int32_t on) {
+  if (!m) return COSK_ERR_ARG;
+  m->prof_on = on != 0;
+  m->prof.clear();
+  m->ev_used = 0;
+  return COSK_OK;
+}
+
+int cosk_profile_read(cosk_model *m, int32_t kind, int32_t block, double *ms, int64_t *launches) {
+  if (!m || !ms || !launches) return COSK_ERR_ARG;
+  cudaSetDevice(m->cfg.device);
+  double tot = 0.0;
+  int64_t cnt = 0;
+  for (size_t i = 0; i + 1 < m->prof.size(); ++i) {
+    const ProfRec &r = m->prof[i];
+    if (r.kind != kind || (block >= 0 && r.block != block)) continue;
+    CK(cudaEventSynchronize(m->prof[i + 1].ev));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.ev, m->prof[i + 1].ev));
+    tot += t;
+    ++cnt;
+  }
+  *ms = tot;
+  *launches = cnt;
+  return COSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// fp32 CUDA-core kernels: input staging, generic graph-conv / temporal-conv tiles for any channel
+// count, pooling + FC, block read-back.  The graph/temporal kernels here serve (a) channel counts
+// the tcgen05 tiles do not cover (the 3-channel first layer, the reference's 2/4-channel test
+// blocks) and (b) as the on-device checker of the tcgen05 kernels (COSK_PATH_SIMT).
+#pragma once
+#include "common.cuh"
+
+namespace cosk {
+
+// ---------------------------------------------------------------------------------------------
+// input: one frame (N, C, V, S) fp32 -> token-major split-bf16 rows, with data_bn folded in.
+// Reference: reshape1 / data_bn / reshape2, models/base.py:73-82 (feature f = s*V*C + v*C + c).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_input(const float *__restrict__ x, long long nc_stride, int C, int V, int S,
+                        const float *__restrict__ scale, const float *__restrict__ shift,
+                        __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cs, long long n_tokens) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tokens * cs) return;
+  long long tok = idx / cs;
+  int c = (int)(idx % cs);
+  float val = 0.f;
+  if (c < C) {
+    long long skel = tok / V;
+    int v = (int)(tok % V);
+    long long n = skel / S;
+    int s = (int)(skel % S);
+    val = x[(n * C + c) * nc_stride + (long long)v * S + s];
+    if (scale != nullptr) {
+      int f = (s * V + v) * C + c;
+      val = val * scale[f] + shift[f];
+    }
+  }
+  __nv_bfloat16 h, l;
+  split_bf16(val, h, l);
+  hi[idx] = h;
+  lo[idx] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared 128x64 register-tiled fp32 GEMM step: acc[8][4] += As[k][row] * Bs[k][col], k < 16.
+// 256 threads: ty = tid / 16 owns rows ty*8..+8, tx = tid % 16 owns cols tx*4..+4.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSimtK = 16;
+constexpr int kSimtN = 64;
+
+__device__ __forceinline__ void simt_mma_chunk(float (&acc)[8][4], const float (*As)[kTileRows],
+                                               const float (*Bs)[kSimtN], int ty, int tx) {
+#pragma unroll
+  for (int k = 0; k < kSimtK; ++k) {
+    float a[8], b[4];
+    const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][ty * 8]);
+    const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][ty * 8 + 4]);
+    const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+    a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+// Load a [16 channels][128 rows] fp32 chunk of a split-bf16 plane pair into smem (transposed).
+__device__ __forceinline__ void simt_load_rows(float (*dst)[kTileRows], const __nv_bfloat16 *__restrict__ hi,
+                                               const __nv_bfloat16 *__restrict__ lo, int cs, int c0, int c_valid,
+                                               long long tok0, int rows_valid) {
+  const int row = threadIdx.x >> 1;
+  const int half = (threadIdx.x & 1) * 8;
+  const bool ok = row < rows_valid;
+  const long long base = (tok0 + row) * cs;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + half + j;
+    float v = 0.f;
+    if (ok && c < c_valid) v = join_bf16(hi[base + c], lo[base + c]);
+    dst[half + j][row] = v;
+  }
+}
+
+// Load a [16][64] chunk of a k-major fp32 weight matrix W[k][n_total].
+__device__ __forceinline__ void simt_load_w(float (*dst)[kSimtN], const float *__restrict__ w, int ld, int k0,
+                                            int k_valid, int n0, int n_total) {
+  const int k = threadIdx.x >> 4;
+  const int n4 = (threadIdx.x & 15) * 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + n4 + j;
+    float v = 0.f;
+    if (k < k_valid && n < n_total) v = w[(long long)(k0 + k) * ld + n];
+    dst[k][n4 + j] = v;
+  }
+}
+
+struct GcnArgs {
+  const __nv_bfloat16 *x_hi, *x_lo;  // block input rows
+  int cs_in, cin;
+  __nv_bfloat16 *y_hi, *y_lo;  // temporal-ring slot
+  int cs_out, cout;
+  const float *w;     // [3*cin (+cin)][cout]  k-major, BN folded
+  const float *bias;  // [cout]
+  int res_conv;       // 1: rows 3*cin.. of w are the folded gcn_residual 1x1 conv (cin != cout)
+  int res_identity;   // 1: add x (cin == cout)
+  const int *mix_ptr;  // CSR over (partition, output vertex): sources and coefficients of A*graph_attn
+  const int *mix_src;
+  const float *mix_val;
+  int V;
+  long long n_tokens;
+  int tile_tokens;
+};
+
+// Graph convolution of one frame: z = sum_i W_i (x A_i) ; BN ; + gcn_residual(x) ; ReLU
+// (GraphConvolution.forward, models/base.py:260-270), one 128-token x 64-channel tile per CTA.
+__global__ void __launch_bounds__(256) k_gcn_simt(GcnArgs a) {
+  __shared__ __align__(16) float Xs[kSimtK][kTileRows];
+  __shared__ __align__(16) float As[kSimtK][kTileRows];
+  __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  const int n0 = blockIdx.y * kSimtN;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int parts = 3 + a.res_conv;
+  for (int c0 = 0; c0 < a.cin; c0 += kSimtK) {
+    __syncthreads();
+    simt_load_rows(Xs, a.x_hi, a.x_lo, a.cs_in, c0, a.cin, tok0, rows_valid);
+    __syncthreads();
+    const int kv = min(kSimtK, a.cin - c0);
+    for (int part = 0; part < parts; ++part) {
+      if (part < 3) {
+        // adjacency mix of this partition: As[k][w] = sum_v A_eff[part][v][w] * Xs[k][v]
+        const int row = threadIdx.x >> 1;
+        const int half = (threadIdx.x & 1) * 8;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = 0.f;
+        if (row < rows_valid) {
+          const int wv = row % a.V;
+          const int sk0 = row - wv;
+          const int e1 = a.mix_ptr[part * a.V + wv + 1];
+          for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) {
+            const int src = sk0 + a.mix_src[e];
+            const float coef = a.mix_val[e];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = fmaf(coef, Xs[half + j][src], m[j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[half + j][row] = m[j];
+      }
+      simt_load_w(Bs, a.w, a.cout, part * a.cin + c0, kv, n0, a.cout);
+      __syncthreads();
+      simt_mma_chunk(acc, part < 3 ? As : Xs, Bs, ty, tx);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = ty * 8 + i;
+    if (row >= rows_valid) continue;
+    const long long tok = tok0 + row;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.cout) continue;
+      float v = acc[i][j] + a.bias[n];
+      if (a.res_identity) v += join_bf16(a.x_hi[tok * a.cs_in + n], a.x_lo[tok * a.cs_in + n]);
+      v = fmaxf(v, 0.f);
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      a.y_hi[tok * a.cs_out + n] = h;
+      a.y_lo[tok * a.cs_out + n] = l;
+    }
+  }
+}
+
+struct TcnArgs {
+  const __nv_bfloat16 *tap_hi[kTaps], *tap_lo[kTaps];  // oldest .. newest ring slots
+  int cs, c;                                            // row stride / channels of the ring
+  const float *w;                                       // [9*c][c] k-major (k = tap*c + ci), BN folded
+  const __nv_bfloat16 *r_hi, *r_lo;                     // block input of 4 executions ago
+  int cs_r, cr, res_kind;
+  const float *w_r;   // [cr][c] k-major folded residual conv (res_kind == 2)
+  const float *bias;  // [c]
+  __nv_bfloat16 *y_hi, *y_lo;
+  int cs_out;
+  long long n_tokens;
+  int tile_tokens;
+};
+
+// 9-tap temporal convolution over the ring + BN + delayed residual + ReLU
+// (co.Conv2d step + BatchNorm2d, models/base.py:307-334; residual wiring :412-446).
+__global__ void __launch_bounds__(256) k_tcn_simt(TcnArgs a) {
+  __shared__ __align__(16) float As[kSimtK][kTileRows];
+  __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  const int n0 = blockIdx.y * kSimtN;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int segs = kTaps + (a.res_kind == 2 ? 1 : 0);
+  for (int seg = 0; seg < segs; ++seg) {
+    const bool is_res = seg == kTaps;
+    const __nv_bfloat16 *hi = is_res ? a.r_hi : a.tap_hi[seg];
+    const __nv_bfloat16 *lo = is_res ? a.r_lo : a.tap_lo[seg];
+    const int cs = is_res ? a.cs_r : a.cs;
+    const int cc = is_res ? a.cr : a.c;
+    const float *w = is_res ? a.w_r : a.w + (long long)seg * a.c * a.c;
+    for (int c0 = 0; c0 < cc; c0 += kSimtK) {
+      simt_load_rows(As, hi, lo, cs, c0, cc, tok0, rows_valid);
+      simt_load_w(Bs, w, a.c, c0, min(kSimtK, cc - c0), n0, a.c);
+      __syncthreads();
+      simt_mma_chunk(acc, As, Bs, ty, tx);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = ty * 8 + i;
+    if (row >= rows_valid) continue;
+    const long long tok = tok0 + row;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.c) continue;
+      float v = acc[i][j] + a.bias[n];
+      if (a.res_kind == 1) v += join_bf16(a.r_hi[tok * a.cs_r + n], a.r_lo[tok * a.cs_r + n]);
+      v = fmaxf(v, 0.f);
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      a.y_hi[tok * a.cs_out + n] = h;
+      a.y_lo[tok * a.cs_out + n] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: spatial mean over V and S, sliding temporal mean over the last P pooled vectors, FC.
+// Reference: spatial_pool / co.AvgPool1d / co.Linear, models/base.py:84,97,99.
+// One CTA per stream; window sum kept in fp64 (adding and removing the same fp32 values is then
+// exact, so the running sum cannot drift); class dot products reduced with warp shuffles.
+// ---------------------------------------------------------------------------------------------
+struct HeadArgs {
+  const __nv_bfloat16 *y_hi, *y_lo;
+  int cs, c, V, S;
+  float *ring;   // [P][N][c] pooled vectors
+  double *sum;   // [N][c]     running window sum
+  int slot, P;
+  long long n_streams;
+  int emit;
+  const float *w, *b;  // [classes][c], [classes]
+  int classes;
+  float *out;  // [N][classes]
+};
+
+__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+  extern __shared__ float mean_s[];
+  const long long n = blockIdx.x;
+  const int rows = a.S * a.V;
+  const long long tok0 = n * rows;
+  for (int c = threadIdx.x; c < a.c; c += blockDim.x) {
+    float tot = 0.f;
+    for (int s = 0; s < a.S; ++s) {
+      float part = 0.f;
+      for (int v = 0; v < a.V; ++v) {
+        const long long i = (tok0 + s * a.V + v) * a.cs + c;
+        part += join_bf16(a.y_hi[i], a.y_lo[i]);
+      }
+      tot += part / (float)a.V;
+    }
+    const float h = tot / (float)a.S;
+    const long long ri = ((long long)a.slot * a.n_streams + n) * a.c + c;
+    const float old = a.ring[ri];
+    a.ring[ri] = h;
+    const double s2 = a.sum[n * a.c + c] + ((double)h - (double)old);
+    a.sum[n * a.c + c] = s2;
+    mean_s[c] = (float)(s2 / (double)a.P);
+  }
+  if (!a.emit) return;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < a.classes; k += nw) {
+    float p = 0.f;
+    for (int c = lane; c < a.c; c += 32) p = fmaf(a.w[(long long)k * a.c + c], mean_s[c], p);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) a.out[n * a.classes + k] = p + a.b[k];
+  }
+}
+
+// token-major split-bf16 rows -> fp32 (B, C, V)
+__global__ void k_read_block(const __nv_bfloat16 *__restrict__ hi, const __nv_bfloat16 *__restrict__ lo, int cs, int C,
+                             int V, long long n_tokens, float *__restrict__ dst) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tokens * C) return;
+  const int v = (int)(idx % V);
+  const long long t2 = idx / V;
+  const int c = (int)(t2 % C);
+  const long long skel = t2 / C;
+  const long long i = (skel * V + v) * cs + c;
+  dst[idx] = join_bf16(hi[i], lo[i]);
+}
+
+}  // namespace cosk

@@ -1,0 +1,153 @@
+"""CPU tests of the boundary: the C-ABI library builds for sm_100a, loads and exports every symbol
+include/cosk.h declares; the host mirror has the reference's names, key mapping and geometry; the
+host-side BN folding reproduces the oracle; the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import continual_skeletons_b200 as cs
+from continual_skeletons_b200 import lib as cslib
+from continual_skeletons_b200 import model as csmodel
+from oracle import regular, weights
+from oracle.weights import ArchSpec
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    path = cs.build_library()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "cosk.h")).read()
+    declared = set(re.findall(r"\b(cosk_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(cslib.SYMBOLS), declared ^ set(cslib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.cosk_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.cosk_version()
+
+
+def test_config_struct_matches_header():
+    # 12 int32 fields + 16 blocks of 4 int32
+    assert ctypes.sizeof(cslib.Config) == 4 * (12 + 4 * cslib.MAX_BLOCKS)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    lib = cs.load_library()
+    cfg = cslib.Config()
+    cfg.abi_version, cfg.vertices, cfg.persons, cfg.c_in, cfg.n_blocks, cfg.padding = 1, 25, 1, 4, 1, 4
+    cfg.blocks[0].cin, cfg.blocks[0].cout, cfg.blocks[0].stride, cfg.blocks[0].res_kind = 4, 4, 1, 0
+    h = ctypes.c_void_p()
+    assert lib.cosk_create(ctypes.byref(cfg), ctypes.byref(h)) == -2  # COSK_ERR_CUDA
+    assert not h.value
+    m = cs.CoStGcn()
+    with pytest.raises(cs.CoskError):
+        m.forward_step(torch.rand(2, 3, 25, 2))
+    with pytest.raises(cs.CoskError):
+        m.forward_steps(torch.rand(2, 3, 10, 25, 2))
+
+
+def test_bad_config_rejected():
+    lib = cs.load_library()
+    cfg = cslib.Config()
+    h = ctypes.c_void_p()
+    assert lib.cosk_create(ctypes.byref(cfg), ctypes.byref(h)) == -1  # abi_version 0
+    assert lib.cosk_create(None, ctypes.byref(h)) == -1
+
+
+def test_graph_bit_exact(golden):
+    assert np.array_equal(cs.ntu_graph().A, golden["adjacency"]["ntu"])
+    assert np.array_equal(cs.kinetics_graph().A, golden["adjacency"]["kinetics"])
+    assert cs.ntu_graph().A.dtype == np.float64
+
+
+@pytest.mark.parametrize("cls,arch_fn,geom", [
+    (cs.CoStGcn, weights.cost_gcn_arch, (153, 4, 76, 76, 75, 19)),
+    (cs.CoStGcnMod, weights.cost_gcn_mod_arch, (81, 1, 0, 80, 220, 0)),
+])
+def test_geometry_and_key_mapping(cls, arch_fn, geom):
+    m = cls(cls.configs().default_values())
+    assert (m.receptive_field, m.stride, m.padding, m.delay, m.pool_size, m.pool_padding) == geom
+    assert m.input_shape == (3, 300, 25, 2) and m.output_shape == (60,)
+    m.validate_attributes()
+    own = list(m.state_dict().keys())
+    # nested names of the reference's continual model
+    assert "layers.layer1.gcn.g_conv.0.weight" in own
+    assert "layers.layer2.0.1.tcn.t_conv.weight" in own
+    assert "layers.layer5.0.0.residual.bn.running_var" in own
+    assert "layers.layer8.0.1.gcn.gcn_residual.1.weight" in own
+    sd = weights.make_state_dict(arch_fn(), seed=1, randomize=True)  # regular StGcn keys
+    mapped = m.map_state_dict(sd, strict=True)
+    assert sorted(mapped.keys()) == sorted(own)
+    res = m.load_state_dict(mapped, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    back = m.state_dict()
+    assert torch.equal(back["layers.layer5.0.0.residual.t_conv.weight"], sd["layers.layer5.residual.t_conv.weight"])
+    # already-continual keys pass through unchanged
+    assert list(m.map_state_dict(back).keys()) == own
+
+
+def test_reference_style_init():
+    torch.manual_seed(0)
+    m = cs.CoStGcn()
+    sd = m.state_dict()
+    assert torch.all(sd["layers.layer3.0.1.gcn.bn.weight"] == 1e-6)  # models/base.py:256-257
+    assert torch.all(sd["layers.layer3.0.1.gcn.graph_attn"] == 1)
+    assert torch.all(sd["layers.layer1.tcn.t_conv.bias"] == 0)
+    w = sd["layers.layer9.0.1.tcn.t_conv.weight"]
+    assert abs(float(w.std()) - (2.0 / (256 * 9)) ** 0.5) < 2e-3  # kaiming fan_out
+    assert not sd["layers.layer3.0.1.gcn.A"].requires_grad
+
+
+@pytest.mark.parametrize("cin,cout,stride,residual,pad", [(4, 4, 1, True, 4), (2, 4, 2, True, 4), (3, 8, 1, False, 0)])
+def test_host_bn_folding_matches_oracle(cin, cout, stride, residual, pad):
+    """The folded tensors handed to cosk_load_weights, applied with plain torch ops, reproduce the
+    oracle's graph conv and temporal conv (host logic, no GPU)."""
+    spec = cs.BlockSpec(cin, cout, stride, residual)
+    arch = ArchSpec([weights.BlockSpec(cin, cout, stride, residual)], padding=pad, head=False, block_names=[""])
+    sd = weights.make_state_dict(arch, seed=21, randomize=True)
+    stack = cs.CoStack([spec], padding=pad)
+    prefix = "0." if spec.res_kind == 0 else None
+    mapped = {}
+    for k, v in sd.items():
+        if spec.res_kind == 0:
+            mapped["0." + k] = v
+        elif k.startswith("residual"):
+            mapped["0.0.0." + k] = v
+        else:
+            mapped["0.0.1." + k] = v
+    stack.load_state_dict(mapped, strict=True)
+    f = csmodel._folded_block_tensors(stack._block_modules()[0], spec)
+    x = weights.make_input((2, cin, 12, 25), seed=22)
+    # graph conv with folded tensors
+    mix = f["mix"]
+    parts = [torch.einsum("bctv,vw->bctw", x, mix[i]) for i in range(3)]
+    if cin != cout:
+        parts.append(x)
+    cat = torch.cat(parts, dim=1)  # (B, K, T, V), K partition-major
+    g = torch.relu(torch.einsum("ok,bktv->botv", f["gcn.w"], cat) + f["gcn.b"][None, :, None, None] + (x if cin == cout else 0))
+    want = regular.graph_conv(x, sd, "gcn.")
+    assert torch.allclose(g, want, atol=2e-6 * max(1.0, float(want.abs().max())))
+    # temporal conv (valid, 9 taps, tap-major K) on frames 0..8 -> regular output index 4 - pad... compare unpadded
+    wt = f["tcn.w"].view(cout, 9, cout)
+    win = want[:, :, 0:9]  # (B, C, 9, V)
+    y = torch.einsum("okc,bckv->bov", wt, win) + f["tcn.b"][None, :, None]
+    ref = regular.temporal_conv(want, sd, "tcn.", 1, 0)[:, :, 0]
+    if spec.res_kind == 2:
+        rr = regular.temporal_conv(x[:, :, 4:5], sd, "residual.", 1, 0)[:, :, 0]
+        y = y + torch.einsum("oc,bcv->bov", f["res.w"], x[:, :, 4])
+        ref = ref + rr
+    assert torch.allclose(y, ref, atol=5e-6 * max(1.0, float(ref.abs().max())))
+
+
+def test_unsupported_arguments():
+    m = cs.CoStGcn()
+    with pytest.raises(NotImplementedError):
+        m.forward_steps(torch.rand(1, 3, 4, 25, 2), pad_end=True)
+    with pytest.raises(NotImplementedError):
+        m.forward_step(torch.rand(1, 3, 25, 2), update_state=False)

@@ -1,0 +1,52 @@
+"""world_size-2 gloo test of the only collective on the path: the logits all-gather over a
+stream-sharded batch."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from continual_skeletons_b200 import all_gather_logits, shard_range
+
+
+def test_shard_range_partitions():
+    for n in (1, 2, 7, 4096, 4097):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n_streams, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_streams * 5, dtype=torch.float32).view(n_streams, 5)
+    lo, hi = shard_range(n_streams, rank, world)
+    got = all_gather_logits(full[lo:hi].clone(), n_streams)
+    ret[rank] = bool(torch.equal(got, full))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_all_gather_logits_gloo_world2():
+    for n_streams in (6, 7):  # even and uneven shards
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(2, _free_port(), n_streams, ret), nprocs=2, join=True)
+        assert ret[0] and ret[1]
+
+
+def test_all_gather_is_identity_without_process_group():
+    x = torch.rand(3, 4)
+    assert all_gather_logits(x, 3) is x
