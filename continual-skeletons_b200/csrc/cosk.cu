@@ -265,12 +265,20 @@ int prepare(cosk_model *m) {
     }
     // tensor-core eligibility + weights
     const bool want_tc = c.path == COSK_PATH_AUTO;
-    b.tc_gcn = want_tc && tc_width(bc.cout) && bc.cin % kBK == 0 && b.mix_max_nz <= kMixMaxNz;
+    b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_nz <= kMixMaxNz;
     b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
     if (b.tc_gcn) {
-      std::vector<uint16_t> s = split_rows(b.gcn_w, bc.cout, Kg);
+      // rows regrouped per pass of 64 output channels: row = pass*(P*64) + part*64 + c, K = cin
+      const int P = 3 + res_conv;
+      std::vector<float> re((size_t)P * bc.cout * bc.cin);
+      for (int o = 0; o < bc.cout; ++o)
+        for (int part = 0; part < P; ++part) {
+          const size_t r = (size_t)(o / 64) * (P * 64) + (size_t)part * 64 + (o % 64);
+          memcpy(&re[r * bc.cin], &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
+        }
+      std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
-      if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)Kg, (uint64_t)2 * bc.cout, (uint32_t)bc.cout))) return rc;
+      if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
     }
     if (b.tc_tcn) {
       const int Kr = bc.res_kind == COSK_RES_CONV ? bc.cin : 0;
@@ -328,10 +336,10 @@ int launch_tc_tcn(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
   CK(cudaGetLastError());
   return COSK_OK;
 }
-template <int COUT>
+template <int P>
 int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  k_tc_gcn<COUT><<<grid, 384, TcGcnCfg<COUT>::kSmemBytes, s>>>(args);
+  k_tc_gcn<P><<<grid, 256, TcGcnCfg<P>::kSmemBytes, s>>>(args);
   CK(cudaGetLastError());
   return COSK_OK;
 }
@@ -340,9 +348,8 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_tcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<256>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<64>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<128>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<256>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
   return COSK_OK;
 }
 
@@ -359,7 +366,7 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.x_row = (int)in.row_hi(in_slot);
     a.t_alloc = (int)m->t_alloc;
     a.cin = bc.cin;
-    a.res_conv = res_conv;
+    a.cout = bc.cout;
     a.V = m->cfg.vertices;
     a.n_tiles = m->n_tiles;
     a.tile_tokens = m->tile_tokens;
@@ -375,9 +382,7 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.epi.y_lo = b.ring.lo(ring_slot);
     a.epi.cs_out = b.ring.cs;
     a.dbg = m->d_dbg;
-    if (bc.cout == 64) rc = launch_tc_gcn<64>(m, a, s);
-    else if (bc.cout == 128) rc = launch_tc_gcn<128>(m, a, s);
-    else rc = launch_tc_gcn<256>(m, a, s);
+    rc = res_conv ? launch_tc_gcn<4>(m, a, s) : launch_tc_gcn<3>(m, a, s);
     if (rc) return rc;
   } else {
     GcnArgs a;
@@ -530,7 +535,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
       h.b = m->d_fc_b;
       h.classes = c.classes;
       h.out = out;
-      k_head<<<(unsigned)m->n_streams, 256, last.out.c * sizeof(float), s>>>(h);
+      k_head<<<(unsigned)m->n_streams, 256, (2 * last.out.cs + last.out.c) * sizeof(float), s>>>(h);
       CK(cudaGetLastError());
       m->launches++;
       m->pool_n++;

@@ -266,21 +266,34 @@ struct HeadArgs {
 };
 
 __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
-  extern __shared__ float mean_s[];
+  extern __shared__ float head_s[];
+  float *part = head_s;             // [2][cs] per-thread-half partial spatial means
+  float *mean_s = head_s + 2 * a.cs;  // [c] window mean
   const long long n = blockIdx.x;
-  const int rows = a.S * a.V;
-  const long long tok0 = n * rows;
-  for (int c = threadIdx.x; c < a.c; c += blockDim.x) {
-    float tot = 0.f;
-    for (int s = 0; s < a.S; ++s) {
-      float part = 0.f;
+  const long long tok0 = n * a.S * a.V;
+  const int half = threadIdx.x >> 7, t128 = threadIdx.x & 127;
+  // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
+  for (int cp = t128; cp < a.cs / 2; cp += 128) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int s = half; s < a.S; s += 2) {
+      float p0 = 0.f, p1 = 0.f;
+      const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
+#pragma unroll 5
       for (int v = 0; v < a.V; ++v) {
-        const long long i = (tok0 + s * a.V + v) * a.cs + c;
-        part += join_bf16(a.y_hi[i], a.y_lo[i]);
+        const uint32_t h = *reinterpret_cast<const uint32_t *>(a.y_hi + base + (long long)v * a.cs);
+        const uint32_t l = *reinterpret_cast<const uint32_t *>(a.y_lo + base + (long long)v * a.cs);
+        p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
+        p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
       }
-      tot += part / (float)a.V;
+      t0 += p0 / (float)a.V;
+      t1 += p1 / (float)a.V;
     }
-    const float h = tot / (float)a.S;
+    part[half * a.cs + 2 * cp] = t0;
+    part[half * a.cs + 2 * cp + 1] = t1;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.c; c += blockDim.x) {
+    const float h = (part[c] + part[a.cs + c]) / (float)a.S;
     const long long ri = ((long long)a.slot * a.n_streams + n) * a.c + c;
     const float old = a.ring[ri];
     a.ring[ri] = h;

@@ -7,14 +7,13 @@
 //
 //   k_tc_tcn<COUT>      9-tap temporal conv over the ring (+ folded strided residual conv as extra
 //                       K-blocks) + bias + identity residual + ReLU.     A and B arrive by TMA.
-//   k_tc_gcn<COUT>      graph conv: the adjacency mix x*A_i is applied by CUDA cores while staging
-//                       the A operand (sparse CSR rows held in registers), then 3 (+1) K-blocks per
-//                       64 input channels; bias + identity residual + ReLU; result -> ring slot.
+//   k_tc_gcn<P>         graph conv as GEMM-then-mix: Y = X [W_0|W_1|W_2(|W_r)]^T on tcgen05 for 64
+//                       output channels per pass, then the sparse adjacency row combination of the
+//                       fp32 accumulators in the epilogue (through shared memory, CSR in registers);
+//                       bias + identity residual + ReLU; result -> ring slot.
 //
 // Both are persistent (one CTA per SM loops over token tiles) and warp specialised:
-//   warp 0  TMA producer (activations)     warp 1  MMA issuer + TMEM owner
-//   warp 2  TMA producer (weights, gcn)    warps 4-7  epilogue (TMEM -> registers -> HBM)
-//   warps 8-11 (gcn only) adjacency-mix producers of the A operand
+//   warp 0  TMA producer     warp 1  MMA issuer + TMEM owner     warps 4-7  epilogue
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,12 +30,6 @@ enum : unsigned int {
   kDbgMmaFull = 0x02000000u,
   kDbgMmaTmemEmpty = 0x03000000u,
   kDbgEpiTmemFull = 0x04000000u,
-  kDbgWProdEmpty = 0x05000000u,
-  kDbgMixXFull = 0x06000000u,
-  kDbgMixAEmpty = 0x07000000u,
-  kDbgMmaAFull = 0x08000000u,
-  kDbgMmaXFull = 0x09000000u,
-  kDbgXProdEmpty = 0x0a000000u,
 };
 
 struct PipeState {
@@ -144,10 +137,14 @@ struct TcTcnArgs {
 
 template <int COUT>
 struct TcTcnCfg {
+  // Activations (HBM latency) and weights (L2 latency) travel in separate rings so that the
+  // activation ring can be one stage deeper where shared memory is tight (COUT = 256).
   static constexpr int kBBytes = COUT * kBK * 2;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = COUT == 64 ? 4 : (COUT == 128 ? 3 : 2);
-  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kAStages = COUT == 64 ? 4 : 3;
+  static constexpr int kBStages = COUT == 64 ? 4 : (COUT == 128 ? 3 : 2);
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kAStages * 2 * kABytes;
+  static constexpr int kBarOff = kBOff + kBStages * 2 * kBBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + COUT * 4 + 1024;  // + slack for manual 1024-B alignment
   static constexpr int kTmemCols = 2 * COUT;                     // double-buffered accumulator
@@ -161,9 +158,11 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window: align on the shared address
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
-  uint64_t *empty = full + Cfg::kStages;
-  uint64_t *tfull = empty + Cfg::kStages;
+  uint64_t *afull = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *aempty = afull + Cfg::kAStages;
+  uint64_t *bfull = aempty + Cfg::kAStages;
+  uint64_t *bempty = bfull + Cfg::kBStages;
+  uint64_t *tfull = bempty + Cfg::kBStages;
   uint64_t *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
@@ -171,9 +170,13 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      ptx::mbar_init(&afull[s], 1);
+      ptx::mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      ptx::mbar_init(&bfull[s], 1);
+      ptx::mbar_init(&bempty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
@@ -197,15 +200,15 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
 
   if (warp == 0) {
     if (lane == 0) {
-      PipeState ps;
+      PipeState pa, pb;
       bool ok = true;
       for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
         const int tok0 = tile * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
-          ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
+          ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
           if (!ok) break;
-          const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
-          ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
+          const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
+          ptx::mbar_arrive_expect_tx(&afull[pa.stage], 2 * kABytes);
           const CUtensorMap *tm;
           int c0, row;
           if (kb < kTaps * a.kb_per_tap) {
@@ -218,17 +221,22 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
             c0 = (kb - kTaps * a.kb_per_tap) * kBK;
             row = a.res_row + tok0;
           }
-          ptx::tma_load_2d(st, tm, &full[ps.stage], c0, row);
-          ptx::tma_load_2d(st + kABytes, tm, &full[ps.stage], c0, row + a.t_alloc);
-          ptx::tma_load_2d(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kb * kBK, 0);
-          ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kb * kBK, COUT);
-          ps.advance<Cfg::kStages>();
+          ptx::tma_load_2d(sa, tm, &afull[pa.stage], c0, row);
+          ptx::tma_load_2d(sa + kABytes, tm, &afull[pa.stage], c0, row + a.t_alloc);
+          pa.advance<Cfg::kAStages>();
+          ok = ptx::mbar_wait(&bempty[pb.stage], pb.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)kb);
+          if (!ok) break;
+          const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBBytes;
+          ptx::mbar_arrive_expect_tx(&bfull[pb.stage], 2 * Cfg::kBBytes);
+          ptx::tma_load_2d(sb, &a.tm_w, &bfull[pb.stage], kb * kBK, 0);
+          ptx::tma_load_2d(sb + Cfg::kBBytes, &a.tm_w, &bfull[pb.stage], kb * kBK, COUT);
+          pb.advance<Cfg::kBStages>();
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      PipeState ps;
+      PipeState pa, pb;
       bool ok = true;
       int it = 0;
       for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -238,13 +246,18 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + acc * COUT;
         for (int kb = 0; kb < nkb; ++kb) {
-          ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)kb);
+          ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaFull | (unsigned)kb);
+          if (!ok) break;
+          ok = ptx::mbar_wait(&bfull[pb.stage], pb.phase, a.dbg, kDbgMmaFull | 0x800000u | (unsigned)kb);
           if (!ok) break;
           ptx::tc_fence_after();
-          const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
-          issue_kblock<COUT>(d, st, st + kABytes, st + 2 * kABytes, st + 2 * kABytes + Cfg::kBBytes, kb == 0);
-          ptx::umma_commit(&empty[ps.stage]);
-          ps.advance<Cfg::kStages>();
+          const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
+          const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBBytes;
+          issue_kblock<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBBytes, kb == 0);
+          ptx::umma_commit(&aempty[pa.stage]);
+          ptx::umma_commit(&bempty[pb.stage]);
+          pa.advance<Cfg::kAStages>();
+          pb.advance<Cfg::kBStages>();
         }
         if (ok) ptx::umma_commit(&tfull[acc]);
       }
@@ -273,17 +286,24 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
 }
 
 // =============================================================================================
-// graph conv
+// graph conv: GEMM first, adjacency mix in the epilogue
+//
+//   z[w] = sum_i sum_v A_i[v,w] * (W_i x[v])  (+ W_r x[w])      (models/base.py:262-269, by linearity)
+//
+// Per (tile, pass) work item the mainloop is a pure TMA -> tcgen05 pipeline computing
+// Y = X [128 x cin] * [W_0 | W_1 | W_2 (| W_r)]^T for 64 output channels (N = P*64 accumulator
+// columns, P = 3 or 4).  The epilogue warps pull Y out of TMEM part by part, exchange it through a
+// swizzled shared-memory buffer and apply the sparse row combination (CSR in registers) in fp32 --
+// no bf16 unpack / re-split on the operand path and no extra rounding before the final split.
 // =============================================================================================
 constexpr int kMixMaxNz = 4;  // non-zeros per (partition, output vertex) the register CSR can hold
 
 struct TcGcnArgs {
-  CUtensorMap tm_x;  // block input ring [kOutSlots*2*t_alloc rows][CIN], box {64, 128}
-  CUtensorMap tm_w;  // [2*COUT rows][(3 + res_conv)*CIN], box {64, COUT}
+  CUtensorMap tm_x;  // block input ring [kOutSlots*2*t_alloc rows][cin], box {64, 128}
+  CUtensorMap tm_w;  // [2*P*cout rows][cin], box {64, P*64}; row = pass*(P*64) + part*64 + c; hi rows, then lo rows
   int x_row;         // first row of the hi plane of the input slot
   int t_alloc;
-  int cin;           // multiple of 64
-  int res_conv;      // 1: a 4th K-block per chunk multiplies the raw input with the folded gcn_residual conv
+  int cin, cout;     // multiples of 64
   int V;
   int n_tiles, tile_tokens;
   long long n_tokens;
@@ -294,58 +314,45 @@ struct TcGcnArgs {
   unsigned int *dbg;
 };
 
-template <int COUT>
+template <int P>
 struct TcGcnCfg {
-  static constexpr int kBBytes = COUT * kBK * 2;
-  static constexpr int kXStages = COUT == 256 ? 1 : 2;  // raw input chunks (hi+lo)
-  static constexpr int kAStages = 2;                     // mixed operand (hi+lo)
-  static constexpr int kBStages = COUT == 64 ? 4 : 2;    // weights (hi+lo)
-  static constexpr int kXOff = 0;
-  static constexpr int kAOff = kXOff + kXStages * 2 * kABytes;
-  static constexpr int kBOff = kAOff + kAStages * 2 * kABytes;
-  static constexpr int kBarOff = kBOff + kBStages * 2 * kBBytes;
+  static constexpr int kN = P * 64;
+  static constexpr int kBBytes = kN * kBK * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = 2;
+  static constexpr int kExchOff = kStages * kStageBytes;
+  static constexpr int kExchBytes = kTileRows * 32 * 4;  // one 128-row x 32-float exchange buffer
+  static constexpr int kBarOff = kExchOff + 2 * kExchBytes;
   static constexpr int kBiasOff = kBarOff + 256;
-  static constexpr int kSmemBytes = kBiasOff + COUT * 4 + 1024;
-  static constexpr int kTmemCols = 2 * COUT;
+  static constexpr int kSmemBytes = kBiasOff + 256 * 4 + 1024;
+  static constexpr int kAccStride = 256;
+  static constexpr int kTmemCols = 512;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
 };
 
-// byte offset of the 16-byte chunk (row, chunk) inside a 128-byte-row SWIZZLE_128B tile
+// byte offset of the 16-byte chunk (row, chunk) inside a tile of 128-byte rows with the 128B swizzle
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-template <int COUT>
-__global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
-  using Cfg = TcGcnCfg<COUT>;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int P>
+__global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
+  using Cfg = TcGcnCfg<P>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment in the shared window: align on the shared address
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t *xfull = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
-  uint64_t *xempty = xfull + Cfg::kXStages;
-  uint64_t *afull = xempty + Cfg::kXStages;
-  uint64_t *aempty = afull + Cfg::kAStages;
-  uint64_t *bfull = aempty + Cfg::kAStages;
-  uint64_t *bempty = bfull + Cfg::kBStages;
-  uint64_t *tfull = bempty + Cfg::kBStages;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *empty = full + Cfg::kStages;
+  uint64_t *tfull = empty + Cfg::kStages;
   uint64_t *tempty = tfull + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
   const uint32_t smem_base = ptx::smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int parts = 3 + a.res_conv;
-  const int nchunk = a.cin / kBK;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kXStages; ++s) {
-      ptx::mbar_init(&xfull[s], 1);
-      ptx::mbar_init(&xempty[s], 128 + a.res_conv);  // 128 mix threads (+ the MMA commit of part 3)
-    }
-    for (int s = 0; s < Cfg::kAStages; ++s) {
-      ptx::mbar_init(&afull[s], 128);
-      ptx::mbar_init(&aempty[s], 1);
-    }
-    for (int s = 0; s < Cfg::kBStages; ++s) {
-      ptx::mbar_init(&bfull[s], 1);
-      ptx::mbar_init(&bempty[s], 1);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
@@ -359,114 +366,63 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
     ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bias_s[i] = a.epi.bias[i];
+  for (int i = threadIdx.x; i < a.cout; i += blockDim.x) bias_s[i] = a.epi.bias[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_pass = a.cout / 64;
+  const int nkb = a.cin / kBK;
 
   if (warp == 0) {
-    // ---- raw input chunks -------------------------------------------------------------------
     if (lane == 0) {
       PipeState ps;
       bool ok = true;
       for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
         const int row = a.x_row + tile * a.tile_tokens;
-        for (int kc = 0; kc < nchunk; ++kc) {
-          ok = ptx::mbar_wait(&xempty[ps.stage], ps.phase ^ 1, a.dbg, kDbgXProdEmpty | (unsigned)kc);
-          if (!ok) break;
-          const uint32_t st = smem_base + Cfg::kXOff + ps.stage * 2 * kABytes;
-          ptx::mbar_arrive_expect_tx(&xfull[ps.stage], 2 * kABytes);
-          ptx::tma_load_2d(st, &a.tm_x, &xfull[ps.stage], kc * kBK, row);
-          ptx::tma_load_2d(st + kABytes, &a.tm_x, &xfull[ps.stage], kc * kBK, row + a.t_alloc);
-          ps.advance<Cfg::kXStages>();
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ---- weights ----------------------------------------------------------------------------
-    if (lane == 0) {
-      PipeState ps;
-      bool ok = true;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
-        for (int kc = 0; ok && kc < nchunk; ++kc) {
-          for (int p = 0; p < parts; ++p) {
-            ok = ptx::mbar_wait(&bempty[ps.stage], ps.phase ^ 1, a.dbg, kDbgWProdEmpty | (unsigned)(kc * 4 + p));
+        for (int pass = 0; ok && pass < n_pass; ++pass) {
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(pass * 16 + kc));
             if (!ok) break;
-            const uint32_t st = smem_base + Cfg::kBOff + ps.stage * 2 * Cfg::kBBytes;
-            ptx::mbar_arrive_expect_tx(&bfull[ps.stage], 2 * Cfg::kBBytes);
-            const int k0 = p * a.cin + kc * kBK;
-            ptx::tma_load_2d(st, &a.tm_w, &bfull[ps.stage], k0, 0);
-            ptx::tma_load_2d(st + Cfg::kBBytes, &a.tm_w, &bfull[ps.stage], k0, COUT);
-            ps.advance<Cfg::kBStages>();
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
+            ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
+            ptx::tma_load_2d(st, &a.tm_x, &full[ps.stage], kc * kBK, row);
+            ptx::tma_load_2d(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc);
+            ptx::tma_load_2d(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, pass * Cfg::kN);
+            ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kc * kBK, P * a.cout + pass * Cfg::kN);
+            ps.advance<Cfg::kStages>();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer -------------------------------------------------------------------------
     if (lane == 0) {
-      PipeState px, pa, pb;
+      PipeState ps;
       bool ok = true;
       int it = 0;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
-        if (!ok) break;
-        ptx::tc_fence_after();
-        const uint32_t d = tmem_base + acc * COUT;
-        for (int kc = 0; ok && kc < nchunk; ++kc) {
-          for (int p = 0; p < parts; ++p) {
-            ok = ptx::mbar_wait(&bfull[pb.stage], pb.phase, a.dbg, kDbgMmaFull | (unsigned)(kc * 4 + p));
+      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+        for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
+          const int acc = it & 1;
+          ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
+          if (!ok) break;
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + acc * Cfg::kAccStride;
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(pass * 16 + kc));
             if (!ok) break;
-            const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBBytes;
-            uint32_t sa;
-            if (p < 3) {
-              ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaAFull | (unsigned)(kc * 4 + p));
-              if (!ok) break;
-              sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
-            } else {
-              ok = ptx::mbar_wait(&xfull[px.stage], px.phase, a.dbg, kDbgMmaXFull | (unsigned)kc);
-              if (!ok) break;
-              sa = smem_base + Cfg::kXOff + px.stage * 2 * kABytes;
-            }
             ptx::tc_fence_after();
-            issue_kblock<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBBytes, kc == 0 && p == 0);
-            ptx::umma_commit(&bempty[pb.stage]);
-            pb.advance<Cfg::kBStages>();
-            if (p < 3) {
-              ptx::umma_commit(&aempty[pa.stage]);
-              pa.advance<Cfg::kAStages>();
-            } else {
-              ptx::umma_commit(&xempty[px.stage]);
-            }
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
+            issue_kblock<Cfg::kN>(d, st, st + kABytes, st + 2 * kABytes, st + 2 * kABytes + Cfg::kBBytes, kc == 0);
+            ptx::umma_commit(&empty[ps.stage]);
+            ps.advance<Cfg::kStages>();
           }
-          px.advance<Cfg::kXStages>();
+          if (ok) ptx::umma_commit(&tfull[acc]);
         }
-        if (ok) ptx::umma_commit(&tfull[acc]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ---- epilogue ---------------------------------------------------------------------------
+  } else if (warp >= 4) {
     const int q = warp & 3;
-    bool ok = true;
-    int it = 0;
-    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
-      if (!ok) break;
-      ptx::tc_fence_after();
-      const int row = q * 32 + lane;
-      const long long tok = (long long)tile * a.tile_tokens + row;
-      const bool valid = row < a.tile_tokens && tok < a.n_tokens;
-      epilogue_rows<COUT>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * COUT, bias_s, a.epi, tok, valid);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-    }
-  } else if (warp >= 8) {
-    // ---- adjacency mix: A_part[row w] = sum_v coef(part, v, w) * X[row of v]  ------------------
-    const int row = threadIdx.x - 256;  // 0..127, fixed for the whole kernel
+    const int row = q * 32 + lane;
     const bool live = row < a.tile_tokens;
     const int wv = row % a.V;
     const int sk0 = row - wv;
@@ -483,58 +439,97 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
         coef[p][j] = on ? a.mix_val[e0 + j] : 0.f;
       }
     }
-    PipeState px, pa;
+    uint8_t *exch = smem + Cfg::kExchOff;
+    uint32_t xb = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
-      for (int kc = 0; ok && kc < nchunk; ++kc) {
-        ok = ptx::mbar_wait(&xfull[px.stage], px.phase, a.dbg, kDbgMixXFull | (unsigned)kc);
-        if (!ok) break;
-        const uint8_t *xh = smem + Cfg::kXOff + px.stage * 2 * kABytes;
-        const uint8_t *xl = xh + kABytes;
+    int it = 0;
+    // NOTE: the four epilogue warps meet in a named barrier inside the loop, so a warp whose bounded
+    // wait expired must keep walking the same sequence (without waiting or storing) instead of leaving.
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const long long tok = (long long)tile * a.tile_tokens + row;
+      for (int pass = 0; pass < n_pass; ++pass, ++it) {
+        const int acc = it & 1;
+        if (ok) ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+        const bool valid = ok && live && tok < a.n_tokens;
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccStride;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          float z[32];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgMixAEmpty | (unsigned)(kc * 4 + p));
-          if (!ok) break;
-          uint8_t *ah = smem + Cfg::kAOff + pa.stage * 2 * kABytes;
-          uint8_t *al = ah + kABytes;
-#pragma unroll 2
-          for (int ch = 0; ch < 8; ++ch) {
-            float m[8];
+          for (int j = 0; j < 32; ++j) z[j] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = 0.f;
+          for (int p = 0; p < 3; ++p) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + p * 64 + c * 32, r);
+            ptx::tmem_ld_wait();
+            uint8_t *buf = exch + xb * Cfg::kExchBytes;
+            xb ^= 1;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<uint4 *>(buf + sw128_off(row, ch)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+            epi_bar_sync();  // everyone's rows of this part are in shared memory; also fences reuse of the other buffer
 #pragma unroll
             for (int e = 0; e < kMixMaxNz; ++e) {
               if (e < cnt[p]) {
-                const uint32_t off = sw128_off(src[p][e], ch);
-                const uint4 h = *reinterpret_cast<const uint4 *>(xh + off);
-                const uint4 l = *reinterpret_cast<const uint4 *>(xl + off);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
                 const float cf = coef[p][e];
+                const int sr = src[p][e];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  m[2 * w] = fmaf(cf, bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]), m[2 * w]);
-                  m[2 * w + 1] = fmaf(cf, bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]), m[2 * w + 1]);
+                for (int ch = 0; ch < 8; ++ch) {
+                  const float4 y = *reinterpret_cast<const float4 *>(buf + sw128_off(sr, ch));
+                  z[4 * ch] = fmaf(cf, y.x, z[4 * ch]);
+                  z[4 * ch + 1] = fmaf(cf, y.y, z[4 * ch + 1]);
+                  z[4 * ch + 2] = fmaf(cf, y.z, z[4 * ch + 2]);
+                  z[4 * ch + 3] = fmaf(cf, y.w, z[4 * ch + 3]);
                 }
               }
             }
-            uint32_t oh[4], ol[4];
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const uint32_t h = pack_bf16x2(m[2 * w], m[2 * w + 1]);
-              oh[w] = h;
-              ol[w] = pack_bf16x2(m[2 * w] - bf16_lo_as_float(h), m[2 * w + 1] - bf16_hi_as_float(h));
-            }
-            const uint32_t off = sw128_off(row, ch);
-            *reinterpret_cast<uint4 *>(ah + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            *reinterpret_cast<uint4 *>(al + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
           }
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&afull[pa.stage]);
-          pa.advance<Cfg::kAStages>();
+          if (P == 4) {  // folded gcn_residual 1x1 conv: own row, no mixing
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(taddr + 3 * 64 + c * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] += __uint_as_float(r[j]);
+          }
+          if (valid) {
+            const int c0 = pass * 64 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] += bias_s[c0 + j];
+            if (a.epi.r_hi != nullptr) {
+              const uint4 *ph = reinterpret_cast<const uint4 *>(a.epi.r_hi + tok * a.epi.cs_r + c0);
+              const uint4 *pl = reinterpret_cast<const uint4 *>(a.epi.r_lo + tok * a.epi.cs_r + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 h = ptx::ldg_v4(ph + g), l = ptx::ldg_v4(pl + g);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  z[g * 8 + w * 2] += bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]);
+                  z[g * 8 + w * 2 + 1] += bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]);
+                }
+              }
+            }
+            uint32_t oh[16], ol[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x0 = fmaxf(z[2 * j], 0.f), x1 = fmaxf(z[2 * j + 1], 0.f);
+              const uint32_t h = pack_bf16x2(x0, x1);
+              oh[j] = h;
+              ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
+            }
+            uint4 *qh = reinterpret_cast<uint4 *>(a.epi.y_hi + tok * a.epi.cs_out + c0);
+            uint4 *ql = reinterpret_cast<uint4 *>(a.epi.y_lo + tok * a.epi.cs_out + c0);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              ptx::stg_v4(qh + g, make_uint4(oh[4 * g], oh[4 * g + 1], oh[4 * g + 2], oh[4 * g + 3]));
+              ptx::stg_v4(ql + g, make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]));
+            }
+          }
         }
-        if (!ok) break;
-        ptx::mbar_arrive(&xempty[px.stage]);  // this thread no longer reads the raw chunk
-        px.advance<Cfg::kXStages>();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
       }
     }
   }
