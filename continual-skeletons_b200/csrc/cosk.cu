@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,6 +45,7 @@ struct BlockW {
   int *d_mix_ptr = nullptr, *d_mix_src = nullptr;
   float *d_mix_val = nullptr;
   int mix_max_nz = 0;
+  bool mix_diag0 = true;  // partition 0 has only self links
   // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
   __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
   CUtensorMap map_gcn_w, map_tcn_w;
@@ -62,6 +64,7 @@ struct ProfRec {
 struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
+  int pair_mask = 0;  // (CTA-pair kernels under bring-up: off by default) which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
   std::vector<BlockW> blk;
   std::vector<float> h_bn_scale, h_bn_shift, h_fc_w, h_fc_b;
@@ -230,6 +233,7 @@ int prepare(cosk_model *m) {
     std::vector<int> ptr(3 * V + 1, 0), src;
     std::vector<float> val;
     b.mix_max_nz = 0;
+    b.mix_diag0 = true;
     for (int p = 0; p < 3; ++p)
       for (int w = 0; w < V; ++w) {
         int cnt = 0;
@@ -239,6 +243,7 @@ int prepare(cosk_model *m) {
             src.push_back(v);
             val.push_back(a);
             ++cnt;
+            if (p == 0 && v != w) b.mix_diag0 = false;
           }
         }
         ptr[p * V + w + 1] = (int)src.size();
@@ -268,13 +273,19 @@ int prepare(cosk_model *m) {
     b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_nz <= kMixMaxNz;
     b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
     if (b.tc_gcn) {
-      // rows regrouped per pass of 64 output channels: row = pass*(P*64) + part*64 + c, K = cin
-      const int P = 3 + res_conv;
-      std::vector<float> re((size_t)P * bc.cout * bc.cin);
+      // Rows regrouped per pass of 64 output channels: row = pass*256 + part*64 + c, K = cin.
+      // Part 3 is the gcn_residual branch: the folded 1x1 conv when cin != cout, else the identity
+      // matrix (x = hi + lo passes through the split-precision products exactly), so the epilogue
+      // never has to fetch residual rows.
+      const int P = 4;
+      std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
       for (int o = 0; o < bc.cout; ++o)
         for (int part = 0; part < P; ++part) {
           const size_t r = (size_t)(o / 64) * (P * 64) + (size_t)part * 64 + (o % 64);
-          memcpy(&re[r * bc.cin], &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
+          if (part < 3 || res_conv)
+            memcpy(&re[r * bc.cin], &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
+          else
+            re[r * bc.cin + o] = 1.0f;
         }
       std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
@@ -336,10 +347,20 @@ int launch_tc_tcn(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
   CK(cudaGetLastError());
   return COSK_OK;
 }
+template <int COUT>
+int launch_tc_tcn2(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
+  // CTA pairs: one cluster of 2 per pair of adjacent token tiles, at most one CTA per SM
+  const int n_pairs = (m->n_tiles + 1) / 2;
+  const int max_clusters = m->num_sms / 2;
+  const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+  k_tc_tcn2<COUT><<<grid, 256, TcTcn2Cfg<COUT>::kSmemBytes, s>>>(args);
+  CK(cudaGetLastError());
+  return COSK_OK;
+}
 template <int P>
 int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  k_tc_gcn<P><<<grid, 256, TcGcnCfg<P>::kSmemBytes, s>>>(args);
+  k_tc_gcn<P><<<grid, 384, TcGcnCfg<P>::kSmemBytes, s>>>(args);
   CK(cudaGetLastError());
   return COSK_OK;
 }
@@ -348,7 +369,9 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_tcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<256>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<64>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<128>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<256>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
   return COSK_OK;
 }
@@ -374,15 +397,16 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.mix_ptr = b.d_mix_ptr;
     a.mix_src = b.d_mix_src;
     a.mix_val = b.d_mix_val;
+    a.diag0 = b.mix_diag0 ? 1 : 0;
     a.epi.bias = b.d_gcn_b;
-    a.epi.r_hi = res_conv ? nullptr : in.hi(in_slot);
-    a.epi.r_lo = res_conv ? nullptr : in.lo(in_slot);
+    a.epi.r_hi = nullptr;  // the gcn_residual branch is part 3 of the GEMM
+    a.epi.r_lo = nullptr;
     a.epi.cs_r = in.cs;
     a.epi.y_hi = b.ring.hi(ring_slot);
     a.epi.y_lo = b.ring.lo(ring_slot);
     a.epi.cs_out = b.ring.cs;
     a.dbg = m->d_dbg;
-    rc = res_conv ? launch_tc_gcn<4>(m, a, s) : launch_tc_gcn<3>(m, a, s);
+    rc = launch_tc_gcn<4>(m, a, s);
     if (rc) return rc;
   } else {
     GcnArgs a;
@@ -440,9 +464,16 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
     a.epi.y_lo = b.out.lo(out_slot);
     a.epi.cs_out = b.out.cs;
     a.dbg = m->d_dbg;
-    if (bc.cout == 64) rc = launch_tc_tcn<64>(m, a, s);
-    else if (bc.cout == 128) rc = launch_tc_tcn<128>(m, a, s);
-    else rc = launch_tc_tcn<256>(m, a, s);
+    const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
+    if (pair) {
+      if (bc.cout == 64) rc = launch_tc_tcn2<64>(m, a, s);
+      else if (bc.cout == 128) rc = launch_tc_tcn2<128>(m, a, s);
+      else rc = launch_tc_tcn2<256>(m, a, s);
+    } else {
+      if (bc.cout == 64) rc = launch_tc_tcn<64>(m, a, s);
+      else if (bc.cout == 128) rc = launch_tc_tcn<128>(m, a, s);
+      else rc = launch_tc_tcn<256>(m, a, s);
+    }
     if (rc) return rc;
   } else {
     TcnArgs a;
@@ -594,6 +625,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   m->num_sms = prop.multiProcessorCount;
+  if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   const bool sm100 = prop.major == 10;
   if (!sm100 && cfg->path == COSK_PATH_AUTO) {
     delete m;
@@ -692,7 +724,8 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
   m->skel_per_tile = kTileRows / c.vertices;
   m->tile_tokens = m->skel_per_tile * c.vertices;
   m->n_tiles = (int)((skel + m->skel_per_tile - 1) / m->skel_per_tile);
-  m->t_alloc = round_up((int)((long long)m->n_tiles * m->tile_tokens + (kTileRows - m->tile_tokens)), 8);
+  // +1 tile: with an odd tile count the second CTA of the last pair walks a phantom tile (loads only)
+  m->t_alloc = round_up((int)((long long)(m->n_tiles + 1) * m->tile_tokens + (kTileRows - m->tile_tokens)), 8);
   if ((long long)kRingSlots * 2 * m->t_alloc > 0x7fffffffLL) return fail(m, COSK_ERR_ARG, "too many streams for 32-bit rows");
   int rc = alloc_act(m, m->xin, kOutSlots, c.c_in);
   if (rc) return rc;

@@ -286,6 +286,185 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
 }
 
 // =============================================================================================
+// temporal conv on CTA pairs (cta_group::2): the two CTAs of a cluster take two adjacent token
+// tiles (UMMA M = 256) and each loads only half of every weight K-block (N/2 rows), which halves the
+// weight bytes entering each SM and the weight shared-memory footprint -> deeper pipeline at COUT = 256.
+// Protocol: "full" barriers live in the leader CTA and count the TMA bytes of BOTH CTAs; "empty" and
+// "accumulator full" barriers exist in both CTAs and are signalled by multicast tcgen05.commit;
+// "accumulator empty" lives in the leader and collects the epilogue warps of both CTAs.
+// =============================================================================================
+template <int COUT>
+struct TcTcn2Cfg {
+  static constexpr int kBHalfBytes = (COUT / 2) * kBK * 2;  // one plane, this CTA's half of the weight rows
+  static constexpr int kAStages = 4;
+  static constexpr int kBStages = COUT == 256 ? 3 : 4;
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = kAStages * 2 * kABytes;
+  static constexpr int kBarOff = kBOff + kBStages * 2 * kBHalfBytes;
+  static constexpr int kBiasOff = kBarOff + 256;
+  static constexpr int kSmemBytes = kBiasOff + COUT * 4 + 1024;
+  static constexpr int kTmemCols = 2 * COUT;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+};
+
+template <int COUT>
+__device__ __forceinline__ void issue_kblock_pair(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                  bool first) {
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileRows, COUT);
+  const uint32_t a_sel[3] = {a_hi, a_lo, a_hi};
+  const uint32_t b_sel[3] = {b_hi, b_hi, b_lo};
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+#pragma unroll
+    for (int k = 0; k < kBK / 16; ++k) {
+      const uint64_t da = ptx::umma_desc_sw128(a_sel[p] + k * 32);
+      const uint64_t db = ptx::umma_desc_sw128(b_sel[p] + k * 32);
+      ptx::umma_bf16_pair(tmem_d, da, db, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
+    }
+  }
+}
+
+template <int COUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(const __grid_constant__ TcTcnArgs a) {
+  using Cfg = TcTcn2Cfg<COUT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *afull = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *aempty = afull + Cfg::kAStages;
+  uint64_t *bfull = aempty + Cfg::kAStages;
+  uint64_t *bempty = bfull + Cfg::kBStages;
+  uint64_t *tfull = bempty + Cfg::kBStages;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      ptx::mbar_init(&afull[s], 1);
+      ptx::mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      ptx::mbar_init(&bfull[s], 1);
+      ptx::mbar_init(&bempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 8);  // 4 epilogue warps of each CTA
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tm_ring);
+    ptx::prefetch_tmap(&a.tm_w);
+    if (a.kb_res) ptx::prefetch_tmap(&a.tm_res);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) bias_s[i] = a.epi.bias[i];
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // both CTAs' barriers are initialised before anything signals across the pair
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nkb = kTaps * a.kb_per_tap + a.kb_res;
+  const int n_pairs = (a.n_tiles + 1) / 2;
+  const int n_clusters = gridDim.x / 2;
+  const int cluster_id = blockIdx.x / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState pa, pb;
+      bool ok = true;
+      for (int pr = cluster_id; ok && pr < n_pairs; pr += n_clusters) {
+        const int tok0 = (2 * pr + (int)rank) * a.tile_tokens;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
+          if (!ok) break;
+          const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&afull[pa.stage], 2 * 2 * kABytes);  // bytes of both CTAs
+          const uint32_t fa = ptx::mapa_u32(ptx::smem_u32(&afull[pa.stage]), 0);
+          const CUtensorMap *tm;
+          int c0, row;
+          if (kb < kTaps * a.kb_per_tap) {
+            const int tap = kb / a.kb_per_tap;
+            tm = &a.tm_ring;
+            c0 = (kb - tap * a.kb_per_tap) * kBK;
+            row = a.tap_row[tap] + tok0;
+          } else {
+            tm = &a.tm_res;
+            c0 = (kb - kTaps * a.kb_per_tap) * kBK;
+            row = a.res_row + tok0;
+          }
+          ptx::tma_load_2d_pair(sa, tm, fa, c0, row);
+          ptx::tma_load_2d_pair(sa + kABytes, tm, fa, c0, row + a.t_alloc);
+          pa.advance<Cfg::kAStages>();
+          ok = ptx::mbar_wait(&bempty[pb.stage], pb.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)kb);
+          if (!ok) break;
+          const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBHalfBytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&bfull[pb.stage], 2 * 2 * Cfg::kBHalfBytes);
+          const uint32_t fb = ptx::mapa_u32(ptx::smem_u32(&bfull[pb.stage]), 0);
+          ptx::tma_load_2d_pair(sb, &a.tm_w, fb, kb * kBK, (int)rank * (COUT / 2));
+          ptx::tma_load_2d_pair(sb + Cfg::kBHalfBytes, &a.tm_w, fb, kb * kBK, COUT + (int)rank * (COUT / 2));
+          pb.advance<Cfg::kBStages>();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      PipeState pa, pb;
+      bool ok = true;
+      int it = 0;
+      for (int pr = cluster_id; ok && pr < n_pairs; pr += n_clusters, ++it) {
+        const int acc = it & 1;
+        ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
+        if (!ok) break;
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + acc * COUT;
+        for (int kb = 0; kb < nkb; ++kb) {
+          ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaFull | (unsigned)kb);
+          if (!ok) break;
+          ok = ptx::mbar_wait(&bfull[pb.stage], pb.phase, a.dbg, kDbgMmaFull | 0x800000u | (unsigned)kb);
+          if (!ok) break;
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
+          const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBHalfBytes;
+          issue_kblock_pair<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBHalfBytes, kb == 0);
+          ptx::umma_commit_pair(&aempty[pa.stage], 3);
+          ptx::umma_commit_pair(&bempty[pb.stage], 3);
+          pa.advance<Cfg::kAStages>();
+          pb.advance<Cfg::kBStages>();
+        }
+        if (ok) ptx::umma_commit_pair(&tfull[acc], 3);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    bool ok = true;
+    int it = 0;
+    for (int pr = cluster_id; ok && pr < n_pairs; pr += n_clusters, ++it) {
+      const int acc = it & 1;
+      ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+      if (!ok) break;
+      ptx::tc_fence_after();
+      const int tile = 2 * pr + (int)rank;
+      const int row = q * 32 + lane;
+      const long long tok = (long long)tile * a.tile_tokens + row;
+      const bool valid = tile < a.n_tiles && row < a.tile_tokens && tok < a.n_tokens;
+      epilogue_rows<COUT>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * COUT, bias_s, a.epi, tok, valid);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+// =============================================================================================
 // graph conv: GEMM first, adjacency mix in the epilogue
 //
 //   z[w] = sum_i sum_v A_i[v,w] * (W_i x[v])  (+ W_r x[w])      (models/base.py:262-269, by linearity)
@@ -310,7 +489,8 @@ struct TcGcnArgs {
   const int *mix_ptr;  // CSR over (partition * V + output vertex)
   const int *mix_src;
   const float *mix_val;
-  EpiArgs epi;  // r_hi/r_lo = input rows when cin == cout (identity gcn_residual)
+  int diag0;  // 1: partition 0 only links a vertex to itself (self links): no row exchange needed for it
+  EpiArgs epi;  // r_hi/r_lo unused: the gcn_residual branch (conv or identity) is part 3 of the GEMM
   unsigned int *dbg;
 };
 
@@ -322,7 +502,8 @@ struct TcGcnCfg {
   static constexpr int kStages = 2;
   static constexpr int kExchOff = kStages * kStageBytes;
   static constexpr int kExchBytes = kTileRows * 32 * 4;  // one 128-row x 32-float exchange buffer
-  static constexpr int kBarOff = kExchOff + 2 * kExchBytes;
+  static constexpr int kExchBufs = P == 3 ? 2 : 1;       // per epilogue warp set (double-buffered when it fits)
+  static constexpr int kBarOff = kExchOff + 2 * kExchBufs * kExchBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + 256 * 4 + 1024;
   static constexpr int kAccStride = 256;
@@ -333,10 +514,10 @@ struct TcGcnCfg {
 // byte offset of the 16-byte chunk (row, chunk) inside a tile of 128-byte rows with the 128B swizzle
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 template <int P>
-__global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
+__global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
   using Cfg = TcGcnCfg<P>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -421,38 +602,48 @@ __global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcn
       }
     }
   } else if (warp >= 4) {
+    // Two epilogue warp sets (warps 4-7 and 8-11) alternate work items: set s owns accumulator s, so
+    // each set has a full mainloop period per item and two warps per scheduler hide each other's
+    // TMEM / shared / global latencies.
+    const int set = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool live = row < a.tile_tokens;
     const int wv = row % a.V;
     const int sk0 = row - wv;
-    int cnt[3], src[3][kMixMaxNz];
+    // register CSR of this row's sources: 4 source rows packed per partition, zero coefficient = unused
+    uint32_t srcs[3];
     float coef[3][kMixMaxNz];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
       const int e0 = a.mix_ptr[p * a.V + wv];
-      cnt[p] = live ? a.mix_ptr[p * a.V + wv + 1] - e0 : 0;
+      const int n = live ? a.mix_ptr[p * a.V + wv + 1] - e0 : 0;
+      srcs[p] = 0;
 #pragma unroll
       for (int j = 0; j < kMixMaxNz; ++j) {
-        const bool on = j < cnt[p];
-        src[p][j] = on ? sk0 + a.mix_src[e0 + j] : 0;
+        const bool on = j < n;
+        srcs[p] |= (uint32_t)(on ? sk0 + a.mix_src[e0 + j] : 0) << (8 * j);
         coef[p][j] = on ? a.mix_val[e0 + j] : 0.f;
       }
     }
-    uint8_t *exch = smem + Cfg::kExchOff;
+    const bool diag0 = a.diag0 != 0;
+    const float d0 = coef[0][0];
+    uint8_t *exch = smem + Cfg::kExchOff + set * Cfg::kExchBufs * Cfg::kExchBytes;
+    const int bar_id = 1 + set;
     uint32_t xb = 0;
     bool ok = true;
     int it = 0;
-    // NOTE: the four epilogue warps meet in a named barrier inside the loop, so a warp whose bounded
+    // NOTE: the four warps of a set meet in a named barrier inside the loop, so a warp whose bounded
     // wait expired must keep walking the same sequence (without waiting or storing) instead of leaving.
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const long long tok = (long long)tile * a.tile_tokens + row;
-      for (int pass = 0; pass < n_pass; ++pass, ++it) {
-        const int acc = it & 1;
-        if (ok) ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const int my = it++;
+        if ((my & 1) != set) continue;
+        if (ok) ok = ptx::mbar_wait(&tfull[set], (my >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)my);
         const bool valid = ok && live && tok < a.n_tokens;
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccStride;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * Cfg::kAccStride;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           float z[32];
@@ -463,17 +654,24 @@ __global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcn
             uint32_t r[32];
             ptx::tmem_ld_32x32(taddr + p * 64 + c * 32, r);
             ptx::tmem_ld_wait();
+            if (p == 0 && diag0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) z[j] = fmaf(d0, __uint_as_float(r[j]), z[j]);
+              continue;
+            }
             uint8_t *buf = exch + xb * Cfg::kExchBytes;
-            xb ^= 1;
+            if (Cfg::kExchBufs == 2) xb ^= 1;
+            else epi_bar_sync(bar_id);  // single buffer: the previous gather must be finished everywhere
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch)
               *reinterpret_cast<uint4 *>(buf + sw128_off(row, ch)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
-            epi_bar_sync();  // everyone's rows of this part are in shared memory; also fences reuse of the other buffer
+            epi_bar_sync(bar_id);  // the set's rows of this part are in shared memory (and, with two
+                                   // buffers, everyone is done reading the buffer written next)
 #pragma unroll
             for (int e = 0; e < kMixMaxNz; ++e) {
-              if (e < cnt[p]) {
-                const float cf = coef[p][e];
-                const int sr = src[p][e];
+              const float cf = coef[p][e];
+              if (cf != 0.f) {
+                const int sr = (int)((srcs[p] >> (8 * e)) & 0xffu);
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch) {
                   const float4 y = *reinterpret_cast<const float4 *>(buf + sw128_off(sr, ch));
@@ -496,20 +694,6 @@ __global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcn
             const int c0 = pass * 64 + c * 32;
 #pragma unroll
             for (int j = 0; j < 32; ++j) z[j] += bias_s[c0 + j];
-            if (a.epi.r_hi != nullptr) {
-              const uint4 *ph = reinterpret_cast<const uint4 *>(a.epi.r_hi + tok * a.epi.cs_r + c0);
-              const uint4 *pl = reinterpret_cast<const uint4 *>(a.epi.r_lo + tok * a.epi.cs_r + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 h = ptx::ldg_v4(ph + g), l = ptx::ldg_v4(pl + g);
-                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  z[g * 8 + w * 2] += bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]);
-                  z[g * 8 + w * 2 + 1] += bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]);
-                }
-              }
-            }
             uint32_t oh[16], ol[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -529,7 +713,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_gcn(const __grid_constant__ TcGcn
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+        if (lane == 0) ptx::mbar_arrive(&tempty[set]);
       }
     }
   }
