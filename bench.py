@@ -34,6 +34,9 @@ ALGO = {
     "cost_gcn_mod": {"state": 3.072e6, "io": 600 + 240 + 2048, "flops": 318.0e6, "warm": 300, "period": 1},
 }
 NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*"}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams, from the `ncu --set full` captures
+# summarised in profiles/ (r1e_ncu_full_summary.csv); None where no capture exists for the kernel.
+NCU_TRAFFIC = {}
 
 
 def load_peaks():
@@ -278,6 +281,15 @@ def run_ours(args, rank, world, local_rank):
     k_bytes = frames_moved * tokens * cout * 4.0
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = k_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    # tensor side of the same kernel: credited = 1-product FLOPs of the reference math; issued = the three
+    # split-precision products actually executed on the 128-row tiles (125 valid rows per tile)
+    cin = [C_IN, 64, 64, 64, 64, 128, 128, 128, 256, 256][kblock]
+    res_k = cin if kblock in (4, 7) else 0
+    k_macs = tokens * cout * ((9 * cout + res_k) if kname == "tcn" else (3 * cin + (cin if cin != cout else 0)))
+    k_tf_credit = 2.0 * k_macs / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
+    issued_k = (9 * cout + res_k) if kname == "tcn" else 4 * cin
+    k_tf_issued = 3 * 2.0 * (tokens * 128.0 / 125.0) * cout * issued_k / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
+    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>")
     step_bytes = algo["state"] + algo["io"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -292,8 +304,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {
             "bound": "hbm", "kernel": f"{'k_tc' if args.kernel_path == 'auto' else 'k'}_{kname}<{cout}> (layer {kblock + 1})",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
+            "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
             "peak_source": peaks["source"],
+            "tensor": {"credited_tflops_1product": k_tf_credit, "issued_tflops_3product": k_tf_issued, "peak_tflops": peaks["bf16_tflops"],
+                       "frac_credited": k_tf_credit / peaks["bf16_tflops"], "frac_issued": k_tf_issued / peaks["bf16_tflops"]},
         },
         "step_roofline": {
             "hbm_frac": step_bytes * (value / world) / 1e9 / peaks["hbm_gbs"],

@@ -48,7 +48,7 @@ struct BlockW {
   bool mix_diag0 = true;  // partition 0 has only self links
   // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
   __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
-  CUtensorMap map_gcn_w, map_tcn_w;
+  CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half;  // _half: box of cout/2 rows for the CTA-pair kernel
   bool tc_gcn = false, tc_tcn = false;
   long long n_in = 0, n_out = 0;
   ActBuf ring, out;
@@ -64,7 +64,7 @@ struct ProfRec {
 struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
-  int pair_mask = 0;  // (CTA-pair kernels under bring-up: off by default) which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
+  int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
   std::vector<BlockW> blk;
   std::vector<float> h_bn_scale, h_bn_shift, h_fc_w, h_fc_b;
@@ -302,6 +302,8 @@ int prepare(cosk_model *m) {
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_tcn_w16), s.data(), s.size()))) return rc;
       if ((rc = make_map(m, &b.map_tcn_w, b.d_tcn_w16, (uint64_t)(Kt + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout)))
         return rc;
+      if ((rc = make_map(m, &b.map_tcn_w_half, b.d_tcn_w16, (uint64_t)(Kt + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout / 2)))
+        return rc;
     }
   }
   m->prepared = true;
@@ -428,8 +430,13 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.V = m->cfg.vertices;
     a.n_tokens = m->n_tokens;
     a.tile_tokens = m->tile_tokens;
-    dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
-    k_gcn_simt<<<grid, 256, 0, s>>>(a);
+    const int K = (3 + res_conv) * bc.cin;
+    if (bc.cin <= 8 && res_conv && bc.cout % 32 == 0 && K <= kSmallKMax && m->cfg.path == COSK_PATH_AUTO) {
+      k_gcn_small<<<m->n_tiles, 256, (size_t)(K + 1) * bc.cout * sizeof(float), s>>>(a);
+    } else {
+      dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
+      k_gcn_simt<<<grid, 256, 0, s>>>(a);
+    }
     CK(cudaGetLastError());
   }
   m->launches++;
@@ -466,6 +473,7 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
     a.dbg = m->d_dbg;
     const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
     if (pair) {
+      a.tm_w = b.map_tcn_w_half;  // each CTA of a pair loads its own half of the weight rows
       if (bc.cout == 64) rc = launch_tc_tcn2<64>(m, a, s);
       else if (bc.cout == 128) rc = launch_tc_tcn2<128>(m, a, s);
       else rc = launch_tc_tcn2<256>(m, a, s);

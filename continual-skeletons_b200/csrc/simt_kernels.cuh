@@ -180,6 +180,84 @@ __global__ void __launch_bounds__(256) k_gcn_simt(GcnArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Graph conv for a narrow input (cin <= 8: the 3-channel first layer).  K = (3 + res_conv) * cin <= 32
+// is far below a tensor-core tile, and the kernel is bound by its output write, so each thread simply
+// owns one token row x 32 output channels: mixed inputs and weights sit in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallKMax = 32;
+
+__global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
+  __shared__ float xs[kTileRows][8 + 1];             // normalised input rows
+  __shared__ float xa[kTileRows][kSmallKMax + 1];    // [part-major mixed inputs | raw input]
+  extern __shared__ __align__(16) float w_s[];       // [K][cout] k-major weights, then bias[cout]
+  const int K = (3 + a.res_conv) * a.cin;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  float *bias_s = w_s + K * a.cout;
+  for (int i = threadIdx.x; i < K * a.cout; i += blockDim.x) w_s[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.cout; i += blockDim.x) bias_s[i] = a.bias[i];
+  for (int i = threadIdx.x; i < kTileRows * a.cin; i += blockDim.x) {
+    const int r = i / a.cin, c = i - r * a.cin;
+    float v = 0.f;
+    if (r < rows_valid) v = join_bf16(a.x_hi[(tok0 + r) * a.cs_in + c], a.x_lo[(tok0 + r) * a.cs_in + c]);
+    xs[r][c] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTileRows * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    const int part = k / a.cin, c = k - part * a.cin;
+    float v = 0.f;
+    if (r < rows_valid) {
+      if (part < 3) {
+        const int wv = r % a.V, sk0 = r - wv;
+        const int e1 = a.mix_ptr[part * a.V + wv + 1];
+        for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) v = fmaf(a.mix_val[e], xs[sk0 + a.mix_src[e]][c], v);
+      } else {
+        v = xs[r][c];
+      }
+    }
+    xa[r][k] = v;
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 1;
+  if (r >= rows_valid) return;
+  const long long tok = tok0 + r;
+  for (int n0 = (threadIdx.x & 1) * 32; n0 < a.cout; n0 += 64) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = bias_s[n0 + j];
+    for (int k = 0; k < K; ++k) {
+      const float xv = xa[r][k];
+      const float4 *wr = reinterpret_cast<const float4 *>(&w_s[k * a.cout + n0]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w4 = wr[j];
+        acc[4 * j] = fmaf(xv, w4.x, acc[4 * j]);
+        acc[4 * j + 1] = fmaf(xv, w4.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(xv, w4.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(xv, w4.w, acc[4 * j + 3]);
+      }
+    }
+    uint32_t oh[16], ol[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float x0 = fmaxf(acc[2 * j], 0.f), x1 = fmaxf(acc[2 * j + 1], 0.f);
+      const uint32_t h = pack_bf16x2(x0, x1);
+      oh[j] = h;
+      ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
+    }
+    uint4 *qh = reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + n0);
+    uint4 *ql = reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + n0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      qh[g] = make_uint4(oh[4 * g], oh[4 * g + 1], oh[4 * g + 2], oh[4 * g + 3]);
+      ql[g] = make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]);
+    }
+  }
+}
+
 struct TcnArgs {
   const __nv_bfloat16 *tap_hi[kTaps], *tap_lo[kTaps];  // oldest .. newest ring slots
   int cs, c;                                            // row stride / channels of the ring

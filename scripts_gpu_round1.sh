@@ -1,5 +1,5 @@
 #!/bin/bash
-# One gpurun call: full GPU test suite, smoke, benches (both variants), ncu launch list.
+# One gpurun call: full GPU test suite, smoke, benches (both variants), ncu launch list, ncu full of the graph conv.
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
@@ -11,6 +11,8 @@ run bench_auto_mod 900 python bench.py --workload cost_gcn_mod --steps 100 --war
 COSK_NCU=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file gpurun_out/launches.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 echo "ncu_list rc=$?" >> gpurun_out/summary.txt
+COSK_NCU=1 timeout 900 ncu --profile-from-start off --set full --import-source on --clock-control none \
+   -k regex:"k_tc_gcn|k_gcn_small|k_head" -c 8 -o gpurun_out/prof_gcn python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gcn.log 2>&1
+echo "ncu_gcn rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
-for f in pytest_gpu smoke; do echo "== $f"; tail -25 gpurun_out/$f.log | cut -c1-400; done
-for f in bench_auto bench_auto_mod; do echo "== $f"; tail -2 gpurun_out/$f.log | cut -c1-300; done
+for f in pytest_gpu smoke; do echo "== $f"; tail -12 gpurun_out/$f.log | cut -c1-400; done
