@@ -189,7 +189,6 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = model.launch_count()
-    model.profile(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ncu = os.environ.get("COSK_NCU") == "1"  # profile only the timed steps: ncu --profile-from-start off
     if ncu:
@@ -205,7 +204,13 @@ def run_ours(args, rank, world, local_rank):
     elapsed_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = model.launch_count() - launches0
-    # per-kernel device times from the events the library recorded on the launching stream
+    # ---- timed region 1b: the same K steps again with the library's per-kernel CUDA events on the
+    # launching stream (an event between two kernels serialises them, so this pass is kept out of `value`)
+    model.profile(True)
+    for _ in range(args.steps):
+        step_resident(t)
+        t += 1
+    barrier()
     prof = {}
     for kind, name in ((0, "input"), (1, "gcn"), (2, "tcn"), (3, "head")):
         ms, n = model.profile_read(kind)

@@ -17,6 +17,12 @@ constexpr int kOutSlots = 5;     // block-output ring: newest + 4 delayed (resid
 constexpr int kTaps = 9;         // temporal kernel size (models/base.py:284,310 in the reference)
 constexpr int kResDelay = 4;     // every residual kind reads the block input of 4 executions ago
 
+// Programmatic dependent launch: every kernel of a step is launched with the programmatic-stream-
+// serialization attribute, lets its successor start launching right away (pdl_trigger) and waits for
+// its predecessor's results only after its own prologue (pdl_wait).  Both are no-ops without PDL.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "simt_kernels.cuh"
@@ -64,6 +65,7 @@ struct ProfRec {
 struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
+  int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
   std::vector<BlockW> blk;
@@ -79,6 +81,7 @@ struct cosk_model {
   long long pool_n = 0, frame = 0;
   std::vector<int32_t> last_flags;
   unsigned int *d_dbg = nullptr;
+  unsigned long long *d_trace = nullptr;  // phase timers of the graph-conv kernel (COSK_TRACE=1)
   int64_t launches = 0;
   int64_t state_bytes = 0;
   // profiling
@@ -329,6 +332,23 @@ int zero_state(cosk_model *m, cudaStream_t s) {
   return COSK_OK;
 }
 
+// Every kernel goes through here: with PDL the launch carries the programmatic-stream-serialization
+// attribute (the kernels call griddepcontrol.wait before touching their predecessor's output).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(cosk_model *m, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = m->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int prof_mark(cosk_model *m, int kind, int block, cudaStream_t s) {
   if (!m->prof_on) return COSK_OK;
   if (m->ev_used == m->ev_pool.size()) {
@@ -345,8 +365,7 @@ int prof_mark(cosk_model *m, int kind, int block, cudaStream_t s) {
 template <int COUT>
 int launch_tc_tcn(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  k_tc_tcn<COUT><<<grid, 256, TcTcnCfg<COUT>::kSmemBytes, s>>>(args);
-  CK(cudaGetLastError());
+  CK(launch_k(m, k_tc_tcn<COUT>, dim3(grid), dim3(256), TcTcnCfg<COUT>::kSmemBytes, s, args));
   return COSK_OK;
 }
 template <int COUT>
@@ -355,15 +374,14 @@ int launch_tc_tcn2(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
   const int n_pairs = (m->n_tiles + 1) / 2;
   const int max_clusters = m->num_sms / 2;
   const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
-  k_tc_tcn2<COUT><<<grid, 256, TcTcn2Cfg<COUT>::kSmemBytes, s>>>(args);
-  CK(cudaGetLastError());
+  CK(launch_k(m, k_tc_tcn2<COUT>, dim3(grid), dim3(256), TcTcn2Cfg<COUT>::kSmemBytes, s, args));
   return COSK_OK;
 }
 template <int P>
 int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  k_tc_gcn<P><<<grid, 384, TcGcnCfg<P>::kSmemBytes, s>>>(args);
-  CK(cudaGetLastError());
+  if (m->d_trace) CK(launch_k(m, k_tc_gcn<P, true>, dim3(grid), dim3(384), TcGcnCfg<P>::kSmemBytes, s, args));
+  else CK(launch_k(m, k_tc_gcn<P, false>, dim3(grid), dim3(384), TcGcnCfg<P>::kSmemBytes, s, args));
   return COSK_OK;
 }
 
@@ -374,7 +392,8 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_tcn2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<256>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
   return COSK_OK;
 }
 
@@ -400,6 +419,7 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.mix_src = b.d_mix_src;
     a.mix_val = b.d_mix_val;
     a.diag0 = b.mix_diag0 ? 1 : 0;
+    a.trace = m->d_trace;
     a.epi.bias = b.d_gcn_b;
     a.epi.r_hi = nullptr;  // the gcn_residual branch is part 3 of the GEMM
     a.epi.r_lo = nullptr;
@@ -432,12 +452,11 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.tile_tokens = m->tile_tokens;
     const int K = (3 + res_conv) * bc.cin;
     if (bc.cin <= 8 && res_conv && bc.cout % 32 == 0 && K <= kSmallKMax && m->cfg.path == COSK_PATH_AUTO) {
-      k_gcn_small<<<m->n_tiles, 256, (size_t)(K + 1) * bc.cout * sizeof(float), s>>>(a);
+      CK(launch_k(m, k_gcn_small, dim3(m->n_tiles), dim3(256), (size_t)(K + 1) * bc.cout * sizeof(float), s, a));
     } else {
       dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
-      k_gcn_simt<<<grid, 256, 0, s>>>(a);
+      CK(launch_k(m, k_gcn_simt, grid, dim3(256), 0, s, a));
     }
-    CK(cudaGetLastError());
   }
   m->launches++;
   return COSK_OK;
@@ -505,8 +524,7 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
     a.n_tokens = m->n_tokens;
     a.tile_tokens = m->tile_tokens;
     dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
-    k_tcn_simt<<<grid, 256, 0, s>>>(a);
-    CK(cudaGetLastError());
+    CK(launch_k(m, k_tcn_simt, grid, dim3(256), 0, s, a));
   }
   m->launches++;
   return COSK_OK;
@@ -522,10 +540,9 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const long long total = m->n_tokens * m->xin.cs;
     const int threads = 256;
     const long long blocks = (total + threads - 1) / threads;
-    k_input<<<(unsigned)blocks, threads, 0, s>>>(x, nc_stride, c.c_in, c.vertices, c.persons,
-                                                c.data_bn ? m->d_bn_scale : nullptr, c.data_bn ? m->d_bn_shift : nullptr,
-                                                m->xin.hi(xslot), m->xin.lo(xslot), m->xin.cs, m->n_tokens);
-    CK(cudaGetLastError());
+    CK(launch_k(m, k_input, dim3((unsigned)blocks), dim3(threads), 0, s, x, (long long)nc_stride, c.c_in, c.vertices, c.persons,
+                (const float *)(c.data_bn ? m->d_bn_scale : nullptr), (const float *)(c.data_bn ? m->d_bn_shift : nullptr),
+                m->xin.hi(xslot), m->xin.lo(xslot), m->xin.cs, m->n_tokens));
     m->launches++;
   }
   const ActBuf *in = &m->xin;
@@ -574,16 +591,14 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
       h.b = m->d_fc_b;
       h.classes = c.classes;
       h.out = out;
-      k_head<<<(unsigned)m->n_streams, 256, (2 * last.out.cs + last.out.c) * sizeof(float), s>>>(h);
-      CK(cudaGetLastError());
+      CK(launch_k(m, k_head, dim3((unsigned)m->n_streams), dim3(256), (2 * last.out.cs + last.out.c) * sizeof(float), s, h));
       m->launches++;
       m->pool_n++;
     } else {
       emit = 1;
       const long long total = m->n_tokens * last.out.c;
-      k_read_block<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(last.out.hi(slot), last.out.lo(slot), last.out.cs,
-                                                                  last.out.c, c.vertices, m->n_tokens, out);
-      CK(cudaGetLastError());
+      CK(launch_k(m, k_read_block, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const __nv_bfloat16 *)last.out.hi(slot),
+                  (const __nv_bfloat16 *)last.out.lo(slot), last.out.cs, last.out.c, c.vertices, m->n_tokens, out));
       m->launches++;
     }
   }
@@ -634,6 +649,11 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   cudaGetDeviceProperties(&prop, cfg->device);
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
+  if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_TRACE")) {
+    if (atoi(e) && cudaMalloc(&m->d_trace, 64 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(m->d_trace, 0, 64 * sizeof(unsigned long long));
+  }
   const bool sm100 = prop.major == 10;
   if (!sm100 && cfg->path == COSK_PATH_AUTO) {
     delete m;
@@ -683,6 +703,7 @@ void cosk_destroy(cosk_model *m) {
   dfree(m->d_fc_w);
   dfree(m->d_fc_b);
   dfree(m->d_dbg);
+  dfree(m->d_trace);
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   delete m;
 }
@@ -809,9 +830,9 @@ int cosk_read_block(cosk_model *m, int32_t block, float *dst_dev, void *stream) 
   cudaSetDevice(m->cfg.device);
   const int slot = (int)((b.n_out - 1) % kOutSlots);
   const long long total = m->n_tokens * b.out.c;
-  k_read_block<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(b.out.hi(slot), b.out.lo(slot), b.out.cs,
-                                                                                 b.out.c, m->cfg.vertices, m->n_tokens, dst_dev);
-  CK(cudaGetLastError());
+  CK(launch_k(m, k_read_block, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+              (const __nv_bfloat16 *)b.out.hi(slot), (const __nv_bfloat16 *)b.out.lo(slot), b.out.cs, b.out.c, m->cfg.vertices,
+              m->n_tokens, dst_dev));
   m->launches++;
   return COSK_OK;
 }
@@ -829,6 +850,14 @@ int cosk_device_error(cosk_model *m, uint32_t *code) {
   unsigned int h[4] = {0, 0, 0, 0};
   CK(cudaMemcpy(h, m->d_dbg, sizeof h, cudaMemcpyDeviceToHost));
   *code = h[0];
+  return COSK_OK;
+}
+
+int cosk_trace_read(cosk_model *m, uint64_t *out, int32_t n) {
+  if (!m || !out || n < 1) return COSK_ERR_ARG;
+  if (!m->d_trace) return fail(m, COSK_ERR_STATE, "tracing is off (set COSK_TRACE=1 before cosk_create)");
+  cudaSetDevice(m->cfg.device);
+  CK(cudaMemcpy(out, m->d_trace, sizeof(uint64_t) * (size_t)(n < 64 ? n : 64), cudaMemcpyDeviceToHost));
   return COSK_OK;
 }
 

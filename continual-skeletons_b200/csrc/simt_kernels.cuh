@@ -14,6 +14,8 @@ namespace cosk {
 __global__ void k_input(const float *__restrict__ x, long long nc_stride, int C, int V, int S,
                         const float *__restrict__ scale, const float *__restrict__ shift,
                         __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cs, long long n_tokens) {
+  pdl_trigger();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tokens * cs) return;
   long long tok = idx / cs;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(256) k_gcn_simt(GcnArgs a) {
   __shared__ __align__(16) float Xs[kSimtK][kTileRows];
   __shared__ __align__(16) float As[kSimtK][kTileRows];
   __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  pdl_trigger();
+  pdl_wait();
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
   const int n0 = blockIdx.y * kSimtN;
@@ -196,8 +200,10 @@ __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
   long long remain = a.n_tokens - tok0;
   const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
   float *bias_s = w_s + K * a.cout;
+  pdl_trigger();
   for (int i = threadIdx.x; i < K * a.cout; i += blockDim.x) w_s[i] = a.w[i];
   for (int i = threadIdx.x; i < a.cout; i += blockDim.x) bias_s[i] = a.bias[i];
+  pdl_wait();  // weights above are static; the input rows below come from the previous kernel
   for (int i = threadIdx.x; i < kTileRows * a.cin; i += blockDim.x) {
     const int r = i / a.cin, c = i - r * a.cin;
     float v = 0.f;
@@ -277,6 +283,8 @@ struct TcnArgs {
 __global__ void __launch_bounds__(256) k_tcn_simt(TcnArgs a) {
   __shared__ __align__(16) float As[kSimtK][kTileRows];
   __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  pdl_trigger();
+  pdl_wait();
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
   const int n0 = blockIdx.y * kSimtN;
@@ -345,6 +353,8 @@ struct HeadArgs {
 
 __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
   extern __shared__ float head_s[];
+  pdl_trigger();
+  pdl_wait();
   float *part = head_s;             // [2][cs] per-thread-half partial spatial means
   float *mean_s = head_s + 2 * a.cs;  // [c] window mean
   const long long n = blockIdx.x;
@@ -394,6 +404,8 @@ __global__ void __launch_bounds__(256) k_head(HeadArgs a) {
 // token-major split-bf16 rows -> fp32 (B, C, V)
 __global__ void k_read_block(const __nv_bfloat16 *__restrict__ hi, const __nv_bfloat16 *__restrict__ lo, int cs, int C,
                              int V, long long n_tokens, float *__restrict__ dst) {
+  pdl_trigger();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tokens * C) return;
   const int v = (int)(idx % V);

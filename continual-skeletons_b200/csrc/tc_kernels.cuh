@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
   const uint32_t smem_base = ptx::smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kAStages; ++s) {
       ptx::mbar_init(&afull[s], 1);
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const int nkb = kTaps * a.kb_per_tap + a.kb_res;
 
   if (warp == 0) {
@@ -221,15 +223,17 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
             c0 = (kb - kTaps * a.kb_per_tap) * kBK;
             row = a.res_row + tok0;
           }
-          ptx::tma_load_2d(sa, tm, &afull[pa.stage], c0, row);
-          ptx::tma_load_2d(sa + kABytes, tm, &afull[pa.stage], c0, row + a.t_alloc);
+          // ring history and delayed residual are read once per step: stream them (evict-first) so the
+          // frames written moments ago by the previous kernel stay in L2 until they are consumed
+          ptx::tma_load_2d_hint(sa, tm, &afull[pa.stage], c0, row, ptx::kEvictFirst);
+          ptx::tma_load_2d_hint(sa + kABytes, tm, &afull[pa.stage], c0, row + a.t_alloc, ptx::kEvictFirst);
           pa.advance<Cfg::kAStages>();
           ok = ptx::mbar_wait(&bempty[pb.stage], pb.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)kb);
           if (!ok) break;
           const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBBytes;
           ptx::mbar_arrive_expect_tx(&bfull[pb.stage], 2 * Cfg::kBBytes);
-          ptx::tma_load_2d(sb, &a.tm_w, &bfull[pb.stage], kb * kBK, 0);
-          ptx::tma_load_2d(sb + Cfg::kBBytes, &a.tm_w, &bfull[pb.stage], kb * kBK, COUT);
+          ptx::tma_load_2d_hint(sb, &a.tm_w, &bfull[pb.stage], kb * kBK, 0, ptx::kEvictLast);
+          ptx::tma_load_2d_hint(sb + Cfg::kBBytes, &a.tm_w, &bfull[pb.stage], kb * kBK, COUT, ptx::kEvictLast);
           pb.advance<Cfg::kBStages>();
         }
       }
@@ -342,6 +346,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
   const bool leader = rank == 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kAStages; ++s) {
       ptx::mbar_init(&afull[s], 1);
@@ -369,6 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
   ptx::cluster_sync_all();  // both CTAs' barriers are initialised before anything signals across the pair
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const int nkb = kTaps * a.kb_per_tap + a.kb_res;
   const int n_pairs = (a.n_tiles + 1) / 2;
   const int n_clusters = gridDim.x / 2;
@@ -398,16 +404,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
             c0 = (kb - kTaps * a.kb_per_tap) * kBK;
             row = a.res_row + tok0;
           }
-          ptx::tma_load_2d_pair(sa, tm, fa, c0, row);
-          ptx::tma_load_2d_pair(sa + kABytes, tm, fa, c0, row + a.t_alloc);
+          ptx::tma_load_2d_pair_hint(sa, tm, fa, c0, row, ptx::kEvictFirst);
+          ptx::tma_load_2d_pair_hint(sa + kABytes, tm, fa, c0, row + a.t_alloc, ptx::kEvictFirst);
           pa.advance<Cfg::kAStages>();
           ok = ptx::mbar_wait(&bempty[pb.stage], pb.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)kb);
           if (!ok) break;
           const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBHalfBytes;
           if (leader) ptx::mbar_arrive_expect_tx(&bfull[pb.stage], 2 * 2 * Cfg::kBHalfBytes);
           const uint32_t fb = ptx::mapa_u32(ptx::smem_u32(&bfull[pb.stage]), 0);
-          ptx::tma_load_2d_pair(sb, &a.tm_w, fb, kb * kBK, (int)rank * (COUT / 2));
-          ptx::tma_load_2d_pair(sb + Cfg::kBHalfBytes, &a.tm_w, fb, kb * kBK, COUT + (int)rank * (COUT / 2));
+          ptx::tma_load_2d_pair_hint(sb, &a.tm_w, fb, kb * kBK, (int)rank * (COUT / 2), ptx::kEvictLast);
+          ptx::tma_load_2d_pair_hint(sb + Cfg::kBHalfBytes, &a.tm_w, fb, kb * kBK, COUT + (int)rank * (COUT / 2), ptx::kEvictLast);
           pb.advance<Cfg::kBStages>();
         }
       }
@@ -490,6 +496,7 @@ struct TcGcnArgs {
   const int *mix_src;
   const float *mix_val;
   int diag0;  // 1: partition 0 only links a vertex to itself (self links): no row exchange needed for it
+  unsigned long long *trace;  // optional phase timers written by CTA 0 (COSK_TRACE=1), else nullptr
   EpiArgs epi;  // r_hi/r_lo unused: the gcn_residual branch (conv or identity) is part 3 of the GEMM
   unsigned int *dbg;
 };
@@ -516,7 +523,7 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row *
 
 __device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <int P>
+template <int P, bool TRACE>
 __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
   using Cfg = TcGcnCfg<P>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -530,6 +537,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
   const uint32_t smem_base = ptx::smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       ptx::mbar_init(&full[s], 1);
@@ -552,6 +560,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const int n_pass = a.cout / 64;
   const int nkb = a.cin / kBK;
 
@@ -567,10 +576,13 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
             if (!ok) break;
             const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
             ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
-            ptx::tma_load_2d(st, &a.tm_x, &full[ps.stage], kc * kBK, row);
-            ptx::tma_load_2d(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc);
-            ptx::tma_load_2d(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, pass * Cfg::kN);
-            ptx::tma_load_2d(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kc * kBK, P * a.cout + pass * Cfg::kN);
+            // the input tile is re-read once per pass (L2 hits): keep it until the last pass, then let it go
+            const uint64_t xpol = pass + 1 < n_pass ? ptx::kEvictNormal : ptx::kEvictFirst;
+            ptx::tma_load_2d_hint(st, &a.tm_x, &full[ps.stage], kc * kBK, row, xpol);
+            ptx::tma_load_2d_hint(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc, xpol);
+            ptx::tma_load_2d_hint(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, pass * Cfg::kN, ptx::kEvictLast);
+            ptx::tma_load_2d_hint(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kc * kBK, P * a.cout + pass * Cfg::kN,
+                                  ptx::kEvictLast);
             ps.advance<Cfg::kStages>();
           }
         }
@@ -581,16 +593,23 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
       PipeState ps;
       bool ok = true;
       int it = 0;
+      const bool mtr = TRACE && a.trace != nullptr && blockIdx.x == 0;
+      unsigned long long mt[2] = {0, 0};
+      const long long mstart = mtr ? clock64() : 0;
       for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
         for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
           const int acc = it & 1;
+          const long long m0 = mtr ? clock64() : 0;
           ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
           if (!ok) break;
+          if (mtr) mt[0] += clock64() - m0;
           ptx::tc_fence_after();
           const uint32_t d = tmem_base + acc * Cfg::kAccStride;
           for (int kc = 0; kc < nkb; ++kc) {
+            const long long m1 = mtr ? clock64() : 0;
             ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(pass * 16 + kc));
             if (!ok) break;
+            if (mtr) mt[1] += clock64() - m1;
             ptx::tc_fence_after();
             const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
             issue_kblock<Cfg::kN>(d, st, st + kABytes, st + 2 * kABytes, st + 2 * kABytes + Cfg::kBBytes, kc == 0);
@@ -599,6 +618,11 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
           }
           if (ok) ptx::umma_commit(&tfull[acc]);
         }
+      }
+      if (mtr) {
+        a.trace[16] = mt[0];
+        a.trace[17] = mt[1];
+        a.trace[18] = clock64() - mstart;
       }
     }
   } else if (warp >= 4) {
@@ -633,6 +657,15 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
     uint32_t xb = 0;
     bool ok = true;
     int it = 0;
+    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    unsigned long long tr_t[6] = {0, 0, 0, 0, 0, 0};
+    long long tr_c = 0, tr_start = tr ? clock64() : 0;
+#define TR_LAP(slot)                  \
+  if (tr) {                           \
+    const long long n_ = clock64();   \
+    tr_t[slot] += n_ - tr_c;          \
+    tr_c = n_;                        \
+  }
     // NOTE: the four warps of a set meet in a named barrier inside the loop, so a warp whose bounded
     // wait expired must keep walking the same sequence (without waiting or storing) instead of leaving.
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -640,7 +673,9 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
       for (int pass = 0; pass < n_pass; ++pass) {
         const int my = it++;
         if ((my & 1) != set) continue;
+        if (tr) tr_c = clock64();
         if (ok) ok = ptx::mbar_wait(&tfull[set], (my >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)my);
+        TR_LAP(0)
         const bool valid = ok && live && tok < a.n_tokens;
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * Cfg::kAccStride;
@@ -654,6 +689,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
             uint32_t r[32];
             ptx::tmem_ld_32x32(taddr + p * 64 + c * 32, r);
             ptx::tmem_ld_wait();
+            TR_LAP(1)
             if (p == 0 && diag0) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) z[j] = fmaf(d0, __uint_as_float(r[j]), z[j]);
@@ -667,6 +703,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
               *reinterpret_cast<uint4 *>(buf + sw128_off(row, ch)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
             epi_bar_sync(bar_id);  // the set's rows of this part are in shared memory (and, with two
                                    // buffers, everyone is done reading the buffer written next)
+            TR_LAP(2)
 #pragma unroll
             for (int e = 0; e < kMixMaxNz; ++e) {
               const float cf = coef[p][e];
@@ -683,7 +720,8 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
               }
             }
           }
-          if (P == 4) {  // folded gcn_residual 1x1 conv: own row, no mixing
+          TR_LAP(3)
+          if (P == 4) {  // gcn_residual branch (folded 1x1 conv or identity): own row, no mixing
             uint32_t r[32];
             ptx::tmem_ld_32x32(taddr + 3 * 64 + c * 32, r);
             ptx::tmem_ld_wait();
@@ -714,8 +752,15 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[set]);
+        TR_LAP(4)
       }
     }
+    if (tr) {
+      for (int i = 0; i < 5; ++i) a.trace[set * 8 + i] = tr_t[i];
+      a.trace[set * 8 + 5] = clock64() - tr_start;
+      a.trace[set * 8 + 6] = (unsigned long long)it;
+    }
+#undef TR_LAP
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -344,6 +344,12 @@ class _CoBase(nn.Module):
         e.check(e.lib.cosk_device_error(e.h, ctypes.byref(code)), "cosk_device_error")
         return int(code.value)
 
+    def trace_read(self, n=24):
+        e = self._engine
+        buf = (ctypes.c_uint64 * n)()
+        e.check(e.lib.cosk_trace_read(e.h, buf, n), "cosk_trace_read")
+        return [int(v) for v in buf]
+
     def profile(self, on):
         e = self._engine
         e.check(e.lib.cosk_profile_enable(e.h, 1 if on else 0), "cosk_profile_enable")

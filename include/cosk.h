@@ -132,6 +132,11 @@ int cosk_profile_read(cosk_model *m, int32_t kind, int32_t block, double *ms, in
  * non-zero code means a bounded mbarrier wait expired: results are invalid.  Synchronises. */
 int cosk_device_error(cosk_model *m, uint32_t *code);
 
+/* Phase timers (SM clock cycles, CTA 0) of the last graph-conv launch when the handle was created with
+ * COSK_TRACE=1 in the environment: [0..6] epilogue set 0 {wait acc, tmem ld, exchange, gather, store,
+ * total, items}, [8..14] set 1, [16..18] MMA thread {wait acc free, wait operands, total}.  Debug aid. */
+int cosk_trace_read(cosk_model *m, uint64_t *out, int32_t n);
+
 const char *cosk_last_error(const cosk_model *m);
 const char *cosk_version(void);
 
