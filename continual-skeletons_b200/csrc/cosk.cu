@@ -46,6 +46,8 @@ struct BlockW {
   int *d_mix_ptr = nullptr, *d_mix_src = nullptr;
   float *d_mix_val = nullptr;
   int mix_max_nz = 0;
+  int gcn_parts = 4;  // accumulator column groups of the tensor-core graph conv (3 or 4)
+  int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
   bool mix_diag0 = true;  // partition 0 has only self links
   // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
   __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
@@ -65,6 +67,7 @@ struct ProfRec {
 struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
+  int gcn_identity_mma = 1;  // identity gcn_residual as a 4th GEMM column group (COSK_GCN_IDENTITY_MMA=0: add input rows instead)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
@@ -252,6 +255,11 @@ int prepare(cosk_model *m) {
         ptr[p * V + w + 1] = (int)src.size();
         if (cnt > b.mix_max_nz) b.mix_max_nz = cnt;
       }
+    b.mix_max_row12 = 0;
+    for (int w = 0; w < V; ++w) {
+      const int n12 = ptr[2 * V + w + 1] - ptr[2 * V + w] + ptr[V + w + 1] - ptr[V + w];
+      if (n12 > b.mix_max_row12) b.mix_max_row12 = n12;
+    }
     if (src.empty()) {
       src.push_back(0);
       val.push_back(0.f);
@@ -273,14 +281,15 @@ int prepare(cosk_model *m) {
     }
     // tensor-core eligibility + weights
     const bool want_tc = c.path == COSK_PATH_AUTO;
-    b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_nz <= kMixMaxNz;
+    b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
     b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
     if (b.tc_gcn) {
-      // Rows regrouped per pass of 64 output channels: row = pass*256 + part*64 + c, K = cin.
+      // Rows regrouped per pass of 64 output channels: row = pass*(P*64) + part*64 + c, K = cin.
       // Part 3 is the gcn_residual branch: the folded 1x1 conv when cin != cout, else the identity
-      // matrix (x = hi + lo passes through the split-precision products exactly), so the epilogue
-      // never has to fetch residual rows.
-      const int P = 4;
+      // matrix (x = hi + lo passes through the split-precision products exactly).  The P = 3 variant of
+      // the kernel (identity added from the input rows by the drain warps) exists but measured slower:
+      // its row-per-thread global loads cost more load/store-unit cycles than the extra MMA columns.
+      const int P = b.gcn_parts = (res_conv || m->gcn_identity_mma) ? 4 : 3;
       std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
       for (int o = 0; o < bc.cout; ++o)
         for (int part = 0; part < P; ++part) {
@@ -380,8 +389,8 @@ int launch_tc_tcn2(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
 template <int P>
 int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  if (m->d_trace) CK(launch_k(m, k_tc_gcn<P, true>, dim3(grid), dim3(384), TcGcnCfg<P>::kSmemBytes, s, args));
-  else CK(launch_k(m, k_tc_gcn<P, false>, dim3(grid), dim3(384), TcGcnCfg<P>::kSmemBytes, s, args));
+  if (m->d_trace) CK(launch_k(m, k_tc_gcn<P, true>, dim3(grid), dim3(512), TcGcnCfg<P>::kSmemBytes, s, args));
+  else CK(launch_k(m, k_tc_gcn<P, false>, dim3(grid), dim3(512), TcGcnCfg<P>::kSmemBytes, s, args));
   return COSK_OK;
 }
 
@@ -392,6 +401,8 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_tcn2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<256>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
   return COSK_OK;
@@ -418,17 +429,16 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.mix_ptr = b.d_mix_ptr;
     a.mix_src = b.d_mix_src;
     a.mix_val = b.d_mix_val;
-    a.diag0 = b.mix_diag0 ? 1 : 0;
     a.trace = m->d_trace;
     a.epi.bias = b.d_gcn_b;
-    a.epi.r_hi = nullptr;  // the gcn_residual branch is part 3 of the GEMM
-    a.epi.r_lo = nullptr;
+    a.epi.r_hi = b.gcn_parts == 4 ? nullptr : in.hi(in_slot);  // P = 3: identity gcn_residual added by the drain warps
+    a.epi.r_lo = b.gcn_parts == 4 ? nullptr : in.lo(in_slot);
     a.epi.cs_r = in.cs;
     a.epi.y_hi = b.ring.hi(ring_slot);
     a.epi.y_lo = b.ring.lo(ring_slot);
     a.epi.cs_out = b.ring.cs;
     a.dbg = m->d_dbg;
-    rc = launch_tc_gcn<4>(m, a, s);
+    rc = b.gcn_parts == 4 ? launch_tc_gcn<4>(m, a, s) : launch_tc_gcn<3>(m, a, s);
     if (rc) return rc;
   } else {
     GcnArgs a;
@@ -650,6 +660,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_GCN_IDENTITY_MMA")) m->gcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_TRACE")) {
     if (atoi(e) && cudaMalloc(&m->d_trace, 64 * sizeof(unsigned long long)) == cudaSuccess)
       cudaMemset(m->d_trace, 0, 64 * sizeof(unsigned long long));

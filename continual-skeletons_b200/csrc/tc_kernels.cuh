@@ -30,6 +30,8 @@ enum : unsigned int {
   kDbgMmaFull = 0x02000000u,
   kDbgMmaTmemEmpty = 0x03000000u,
   kDbgEpiTmemFull = 0x04000000u,
+  kDbgEpiExchEmpty = 0x05000000u,
+  kDbgEpiExchFull = 0x06000000u,
 };
 
 struct PipeState {
@@ -473,15 +475,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
 // =============================================================================================
 // graph conv: GEMM first, adjacency mix in the epilogue
 //
-//   z[w] = sum_i sum_v A_i[v,w] * (W_i x[v])  (+ W_r x[w])      (models/base.py:262-269, by linearity)
+//   z[w] = sum_i sum_v A_i[v,w] * (W_i x[v])  + gcn_residual(x)[w]      (models/base.py:262-269, by linearity)
 //
 // Per (tile, pass) work item the mainloop is a pure TMA -> tcgen05 pipeline computing
-// Y = X [128 x cin] * [W_0 | W_1 | W_2 (| W_r)]^T for 64 output channels (N = P*64 accumulator
-// columns, P = 3 or 4).  The epilogue warps pull Y out of TMEM part by part, exchange it through a
-// swizzled shared-memory buffer and apply the sparse row combination (CSR in registers) in fp32 --
-// no bf16 unpack / re-split on the operand path and no extra rounding before the final split.
+// Y = X [128 x cin] * [W_0 | W_1 | W_2 (| W_r)]^T for 64 output channels (N = P*64 accumulator columns;
+// P = 4 when gcn_residual is a folded 1x1 conv, P = 3 when it is the identity).  The epilogue is split
+// over two warp roles that hand 16-channel chunks over through shared memory with mbarriers:
+//   drain warps (4, thread = token row): tcgen05.ld the chunk of every part, fold the own-row terms
+//       T = a0[w]*Y0 (+ Y3) + bias, and write the planes T, Y1, Y2 (swizzled 64-byte rows);
+//   mix warps (8, lane = channel, 2 token rows per instruction): z[w] = T[w] + sum over the CSR sources
+//       of partitions 1 and 2 (+ identity residual row from global), ReLU, split, store.
+// The transposed mix phase reads whole 64-byte row segments, so gathering arbitrary source rows is free
+// of bank conflicts and of divergence, and the stores are sector-sized and contiguous.
 // =============================================================================================
-constexpr int kMixMaxNz = 4;  // non-zeros per (partition, output vertex) the register CSR can hold
+
+constexpr int kMixSlots = 6;    // non-zeros of partitions 1 and 2 together per output vertex
+constexpr int kGcnChunk = 16;   // channels handed over per exchange buffer
 
 struct TcGcnArgs {
   CUtensorMap tm_x;  // block input ring [kOutSlots*2*t_alloc rows][cin], box {64, 128}
@@ -492,12 +501,11 @@ struct TcGcnArgs {
   int V;
   int n_tiles, tile_tokens;
   long long n_tokens;
-  const int *mix_ptr;  // CSR over (partition * V + output vertex)
+  const int *mix_ptr;  // CSR over (partition * V + output vertex); partition 0 must be diagonal (self links)
   const int *mix_src;
   const float *mix_val;
-  int diag0;  // 1: partition 0 only links a vertex to itself (self links): no row exchange needed for it
   unsigned long long *trace;  // optional phase timers written by CTA 0 (COSK_TRACE=1), else nullptr
-  EpiArgs epi;  // r_hi/r_lo unused: the gcn_residual branch (conv or identity) is part 3 of the GEMM
+  EpiArgs epi;                // r_hi/r_lo = input rows when cin == cout (identity gcn_residual, P = 3), else nullptr
   unsigned int *dbg;
 };
 
@@ -507,10 +515,13 @@ struct TcGcnCfg {
   static constexpr int kBBytes = kN * kBK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = 2;
+  static constexpr int kPlaneBytes = kTileRows * kGcnChunk * 4;  // 8 KB: 128 rows x 16 floats
+  static constexpr int kExchBytes = 3 * kPlaneBytes;             // planes T, Y1, Y2
+  static constexpr int kExchBufs = P == 3 ? 2 : 1;
   static constexpr int kExchOff = kStages * kStageBytes;
-  static constexpr int kExchBytes = kTileRows * 32 * 4;  // one 128-row x 32-float exchange buffer
-  static constexpr int kExchBufs = P == 3 ? 2 : 1;       // per epilogue warp set (double-buffered when it fits)
-  static constexpr int kBarOff = kExchOff + 2 * kExchBufs * kExchBytes;
+  static constexpr int kCsrOff = kExchOff + kExchBufs * kExchBytes;  // per row: n, src[8] (bytes), coef[8]
+  static constexpr int kCsrBytes = kTileRows * (4 + 4 * kMixSlots) + kTileRows * 8;  // n, coef, src (+ row order)
+  static constexpr int kBarOff = kCsrOff + kCsrBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + 256 * 4 + 1024;
   static constexpr int kAccStride = 256;
@@ -518,13 +529,13 @@ struct TcGcnCfg {
   static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
 };
 
-// byte offset of the 16-byte chunk (row, chunk) inside a tile of 128-byte rows with the 128B swizzle
-__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
-
-__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// byte offset of element (row, col) in an exchange plane: 64-byte rows, 16-byte chunks XOR-swizzled with
+// (row >> 1) so that 8 consecutive rows writing the same chunk, and any two rows of different parity
+// reading whole rows, never meet in a bank
+__device__ __forceinline__ uint32_t exch_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
 template <int P, bool TRACE>
-__global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
+__global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
   using Cfg = TcGcnCfg<P>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -532,8 +543,15 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
   uint64_t *empty = full + Cfg::kStages;
   uint64_t *tfull = empty + Cfg::kStages;
   uint64_t *tempty = tfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  uint64_t *xfull = tempty + 2;
+  uint64_t *xempty = xfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xempty + 2);
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
+  // CSR of partitions 1 and 2 per tile row, shared by the mix warps
+  int *csr_n = reinterpret_cast<int *>(smem + Cfg::kCsrOff);                 // [128]
+  float *csr_coef = reinterpret_cast<float *>(csr_n + kTileRows);             // [8][128]
+  uint8_t *csr_src = reinterpret_cast<uint8_t *>(csr_coef + kMixSlots * kTileRows);  // [slots][128]: plane (bit 7) | source row
+  uint8_t *csr_perm = csr_src + kMixSlots * kTileRows;                               // [128] mix-phase row order
   const uint32_t smem_base = ptx::smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -545,7 +563,9 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
-      ptx::mbar_init(&tempty[s], 4);
+      ptx::mbar_init(&tempty[s], 4);  // the four drain warps
+      ptx::mbar_init(&xfull[s], 4);   // the four drain warps
+      ptx::mbar_init(&xempty[s], 8);  // the eight mix warps
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&a.tm_x);
@@ -556,6 +576,36 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
     ptx::tmem_relinquish();
   }
   for (int i = threadIdx.x; i < a.cout; i += blockDim.x) bias_s[i] = a.epi.bias[i];
+  if (threadIdx.x < kTileRows) {
+    const int row = threadIdx.x;
+    const int wv = row % a.V, sk0 = row - wv;
+    int n = 0;
+    for (int e = 0; e < kMixSlots; ++e) {
+      csr_coef[e * kTileRows + row] = 0.f;
+      csr_src[e * kTileRows + row] = 0;
+    }
+    if (row < a.tile_tokens) {
+      for (int p = 1; p < 3; ++p)
+        for (int e = a.mix_ptr[p * a.V + wv]; e < a.mix_ptr[p * a.V + wv + 1] && n < kMixSlots; ++e) {
+          csr_coef[n * kTileRows + row] = a.mix_val[e];
+          csr_src[n * kTileRows + row] = (uint8_t)(((p - 1) << 7) | (sk0 + a.mix_src[e]));
+          ++n;
+        }
+    }
+    csr_n[row] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x < kTileRows) {
+    // rank of this row when rows are ordered by descending source count (ties by row index): the mix
+    // warps walk rows in that order, so the 8 rows sharing an instruction need about the same slots
+    const int row = threadIdx.x, n = csr_n[row];
+    int rank = 0;
+    for (int r = 0; r < kTileRows; ++r) {
+      const int nr = csr_n[r];
+      rank += (nr > n || (nr == n && r < row)) ? 1 : 0;
+    }
+    csr_perm[rank] = (uint8_t)row;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -563,6 +613,7 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
   pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const int n_pass = a.cout / 64;
   const int nkb = a.cin / kBK;
+  constexpr int kChunks = 64 / kGcnChunk;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -625,142 +676,197 @@ __global__ void __launch_bounds__(384, 1) k_tc_gcn(const __grid_constant__ TcGcn
         a.trace[18] = clock64() - mstart;
       }
     }
-  } else if (warp >= 4) {
-    // Two epilogue warp sets (warps 4-7 and 8-11) alternate work items: set s owns accumulator s, so
-    // each set has a full mainloop period per item and two warps per scheduler hide each other's
-    // TMEM / shared / global latencies.
-    const int set = (warp - 4) >> 2;
+  } else if (warp >= 4 && warp < 8) {
+    // ---- drain: TMEM -> own-row terms folded -> exchange planes --------------------------------
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const bool live = row < a.tile_tokens;
-    const int wv = row % a.V;
-    const int sk0 = row - wv;
-    // register CSR of this row's sources: 4 source rows packed per partition, zero coefficient = unused
-    uint32_t srcs[3];
-    float coef[3][kMixMaxNz];
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const int e0 = a.mix_ptr[p * a.V + wv];
-      const int n = live ? a.mix_ptr[p * a.V + wv + 1] - e0 : 0;
-      srcs[p] = 0;
-#pragma unroll
-      for (int j = 0; j < kMixMaxNz; ++j) {
-        const bool on = j < n;
-        srcs[p] |= (uint32_t)(on ? sk0 + a.mix_src[e0 + j] : 0) << (8 * j);
-        coef[p][j] = on ? a.mix_val[e0 + j] : 0.f;
-      }
+    float d0 = 0.f;  // coefficient of the self link (partition 0 is diagonal)
+    if (row < a.tile_tokens) {
+      const int wv = row % a.V;
+      const int e0 = a.mix_ptr[wv];
+      if (a.mix_ptr[wv + 1] > e0) d0 = a.mix_val[e0];
     }
-    const bool diag0 = a.diag0 != 0;
-    const float d0 = coef[0][0];
-    uint8_t *exch = smem + Cfg::kExchOff + set * Cfg::kExchBufs * Cfg::kExchBytes;
-    const int bar_id = 1 + set;
-    uint32_t xb = 0;
+    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    unsigned long long tr_t[4] = {0, 0, 0, 0};
+    long long tr_c = 0;
+    const long long tr_start = tr ? clock64() : 0;
+    const bool has_res = a.epi.r_hi != nullptr;  // identity gcn_residual (P == 3): own input row, prefetched one chunk ahead
     bool ok = true;
     int it = 0;
-    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
-    unsigned long long tr_t[6] = {0, 0, 0, 0, 0, 0};
-    long long tr_c = 0, tr_start = tr ? clock64() : 0;
-#define TR_LAP(slot)                  \
-  if (tr) {                           \
-    const long long n_ = clock64();   \
-    tr_t[slot] += n_ - tr_c;          \
-    tr_c = n_;                        \
-  }
-    // NOTE: the four warps of a set meet in a named barrier inside the loop, so a warp whose bounded
-    // wait expired must keep walking the same sequence (without waiting or storing) instead of leaving.
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    uint32_t xc = 0;  // exchange chunks handed over so far
+    uint4 xr[4];      // next chunk's residual: 16 channels x {hi, lo} bf16
+    auto fetch_res = [&](int tile, int c0) {
       const long long tok = (long long)tile * a.tile_tokens + row;
-      for (int pass = 0; pass < n_pass; ++pass) {
-        const int my = it++;
-        if ((my & 1) != set) continue;
+      if (has_res && row < a.tile_tokens && tok < a.n_tokens) {
+        const uint4 *ph = reinterpret_cast<const uint4 *>(a.epi.r_hi + tok * a.epi.cs_r + c0);
+        const uint4 *pl = reinterpret_cast<const uint4 *>(a.epi.r_lo + tok * a.epi.cs_r + c0);
+        xr[0] = ptx::ldg_v4(ph);
+        xr[1] = ptx::ldg_v4(ph + 1);
+        xr[2] = ptx::ldg_v4(pl);
+        xr[3] = ptx::ldg_v4(pl + 1);
+      } else {
+        xr[0] = xr[1] = xr[2] = xr[3] = make_uint4(0, 0, 0, 0);
+      }
+    };
+    if (blockIdx.x < a.n_tiles) fetch_res(blockIdx.x, 0);
+    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+      for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
+        const int acc = it & 1;
         if (tr) tr_c = clock64();
-        if (ok) ok = ptx::mbar_wait(&tfull[set], (my >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)my);
-        TR_LAP(0)
-        const bool valid = ok && live && tok < a.n_tokens;
+        ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+        if (!ok) break;
+        if (tr) { const long long n_ = clock64(); tr_t[0] += n_ - tr_c; tr_c = n_; }
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + set * Cfg::kAccStride;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccStride;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          float z[32];
+        for (int c = 0; c < kChunks; ++c, ++xc) {
+          const int c0 = pass * 64 + c * kGcnChunk;
+          float t[16];
+          {  // own-row terms that do not come from TMEM: bias + identity residual (loaded a chunk ago)
+            const uint32_t hw[8] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w};
+            const uint32_t lw[8] = {xr[2].x, xr[2].y, xr[2].z, xr[2].w, xr[3].x, xr[3].y, xr[3].z, xr[3].w};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = 0.f;
-#pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(taddr + p * 64 + c * 32, r);
-            ptx::tmem_ld_wait();
-            TR_LAP(1)
-            if (p == 0 && diag0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) z[j] = fmaf(d0, __uint_as_float(r[j]), z[j]);
-              continue;
-            }
-            uint8_t *buf = exch + xb * Cfg::kExchBytes;
-            if (Cfg::kExchBufs == 2) xb ^= 1;
-            else epi_bar_sync(bar_id);  // single buffer: the previous gather must be finished everywhere
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<uint4 *>(buf + sw128_off(row, ch)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
-            epi_bar_sync(bar_id);  // the set's rows of this part are in shared memory (and, with two
-                                   // buffers, everyone is done reading the buffer written next)
-            TR_LAP(2)
-#pragma unroll
-            for (int e = 0; e < kMixMaxNz; ++e) {
-              const float cf = coef[p][e];
-              if (cf != 0.f) {
-                const int sr = (int)((srcs[p] >> (8 * e)) & 0xffu);
-#pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
-                  const float4 y = *reinterpret_cast<const float4 *>(buf + sw128_off(sr, ch));
-                  z[4 * ch] = fmaf(cf, y.x, z[4 * ch]);
-                  z[4 * ch + 1] = fmaf(cf, y.y, z[4 * ch + 1]);
-                  z[4 * ch + 2] = fmaf(cf, y.z, z[4 * ch + 2]);
-                  z[4 * ch + 3] = fmaf(cf, y.w, z[4 * ch + 3]);
-                }
-              }
+            for (int w = 0; w < 8; ++w) {
+              t[2 * w] = bias_s[c0 + 2 * w] + (bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]));
+              t[2 * w + 1] = bias_s[c0 + 2 * w + 1] + (bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]));
             }
           }
-          TR_LAP(3)
-          if (P == 4) {  // gcn_residual branch (folded 1x1 conv or identity): own row, no mixing
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(taddr + 3 * 64 + c * 32, r);
+          {  // prefetch the residual of the next chunk / pass / tile
+            int nt = tile, nc0 = c0 + kGcnChunk;
+            if (nc0 >= a.cout) {
+              nc0 = 0;
+              nt = tile + gridDim.x;
+            }
+            if (nt < a.n_tiles) fetch_res(nt, nc0);
+          }
+          uint32_t y0[16], y1[16], y2[16];
+          ptx::tmem_ld_32x16(taddr + 0 * 64 + c * kGcnChunk, y0);
+          ptx::tmem_ld_32x16(taddr + 1 * 64 + c * kGcnChunk, y1);
+          ptx::tmem_ld_32x16(taddr + 2 * 64 + c * kGcnChunk, y2);
+          if (P == 4) {
+            uint32_t y3[16];
+            ptx::tmem_ld_32x16(taddr + 3 * 64 + c * kGcnChunk, y3);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] += __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) t[j] += __uint_as_float(y3[j]);
+          } else {
+            ptx::tmem_ld_wait();
           }
-          if (valid) {
-            const int c0 = pass * 64 + c * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] += bias_s[c0 + j];
-            uint32_t oh[16], ol[16];
+          for (int j = 0; j < 16; ++j) t[j] = fmaf(d0, __uint_as_float(y0[j]), t[j]);
+          if (tr) { const long long n_ = clock64(); tr_t[1] += n_ - tr_c; tr_c = n_; }
+          const uint32_t b = Cfg::kExchBufs == 2 ? (xc & 1) : 0;
+          const uint32_t use = Cfg::kExchBufs == 2 ? (xc >> 1) : xc;
+          ok = ptx::mbar_wait(&xempty[b], (use & 1) ^ 1, a.dbg, kDbgEpiExchEmpty | (xc & 0xffff));
+          if (!ok) break;
+          if (tr) { const long long n_ = clock64(); tr_t[2] += n_ - tr_c; tr_c = n_; }
+          uint8_t *buf = smem + Cfg::kExchOff + b * Cfg::kExchBytes;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x0 = fmaxf(z[2 * j], 0.f), x1 = fmaxf(z[2 * j + 1], 0.f);
-              const uint32_t h = pack_bf16x2(x0, x1);
-              oh[j] = h;
-              ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
-            }
-            uint4 *qh = reinterpret_cast<uint4 *>(a.epi.y_hi + tok * a.epi.cs_out + c0);
-            uint4 *ql = reinterpret_cast<uint4 *>(a.epi.y_lo + tok * a.epi.cs_out + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              ptx::stg_v4(qh + g, make_uint4(oh[4 * g], oh[4 * g + 1], oh[4 * g + 2], oh[4 * g + 3]));
-              ptx::stg_v4(ql + g, make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]));
-            }
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t off = exch_off(row, ch);
+            *reinterpret_cast<float4 *>(buf + off) = make_float4(t[4 * ch], t[4 * ch + 1], t[4 * ch + 2], t[4 * ch + 3]);
+            *reinterpret_cast<uint4 *>(buf + Cfg::kPlaneBytes + off) = make_uint4(y1[4 * ch], y1[4 * ch + 1], y1[4 * ch + 2], y1[4 * ch + 3]);
+            *reinterpret_cast<uint4 *>(buf + 2 * Cfg::kPlaneBytes + off) = make_uint4(y2[4 * ch], y2[4 * ch + 1], y2[4 * ch + 2], y2[4 * ch + 3]);
           }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&xfull[b]);
+          if (tr) { const long long n_ = clock64(); tr_t[3] += n_ - tr_c; tr_c = n_; }
         }
+        if (!ok) break;
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty[set]);
-        TR_LAP(4)
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);  // accumulator fully read: the MMA may overwrite it
       }
     }
     if (tr) {
-      for (int i = 0; i < 5; ++i) a.trace[set * 8 + i] = tr_t[i];
-      a.trace[set * 8 + 5] = clock64() - tr_start;
-      a.trace[set * 8 + 6] = (unsigned long long)it;
+      for (int i = 0; i < 4; ++i) a.trace[i] = tr_t[i];
+      a.trace[5] = clock64() - tr_start;
+      a.trace[6] = (unsigned long long)it;
     }
-#undef TR_LAP
+  } else if (warp >= 8) {
+    // ---- mix: one instruction covers 8 token rows x 16 channels (lane = row, 4-channel quad) -----------
+    // A lane always serves the same 2 tile rows (tiles are skeleton aligned), so the byte offsets of its
+    // CSR sources inside an exchange buffer are computed once and live in registers; rows are walked in
+    // the count-sorted order, and (row group, slot) pairs empty for all 8 rows are skipped warp-uniformly.
+    const int m = warp - 8;
+    const int rr = lane >> 2, cq = lane & 3;
+    int rows[2];
+    uint32_t off_t[2], off_s[2][kMixSlots / 2];
+    uint32_t active = 0;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int row = csr_perm[m * 16 + g * 8 + rr];
+      rows[g] = row;
+      off_t[g] = exch_off(row, cq);
+      const int n = csr_n[row];
+#pragma unroll
+      for (int e = 0; e < kMixSlots; ++e) {
+        const bool on = e < n;
+        const uint32_t sp = on ? csr_src[e * kTileRows + row] : 0u;
+        const uint32_t off = on ? (1 + (sp >> 7)) * Cfg::kPlaneBytes + exch_off((int)(sp & 0x7f), cq) : 0u;
+        if (e & 1) off_s[g][e >> 1] |= off << 16;
+        else off_s[g][e >> 1] = off;
+        if (__any_sync(0xffffffffu, on)) active |= 1u << (g * kMixSlots + e);
+      }
+    }
+    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && m == 0 && lane == 0;
+    unsigned long long tr_t[3] = {0, 0, 0};
+    long long tr_c = 0;
+    bool ok = true;
+    uint32_t xc = 0;
+    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+      const long long tok0 = (long long)tile * a.tile_tokens;
+      for (int pass = 0; ok && pass < n_pass; ++pass) {
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++xc) {
+          const int c0 = pass * 64 + c * kGcnChunk + 4 * cq;
+          const uint32_t b = Cfg::kExchBufs == 2 ? (xc & 1) : 0;
+          const uint32_t use = Cfg::kExchBufs == 2 ? (xc >> 1) : xc;
+          if (tr) tr_c = clock64();
+          ok = ptx::mbar_wait(&xfull[b], use & 1, a.dbg, kDbgEpiExchFull | (xc & 0xffff));
+          if (!ok) break;
+          if (tr) { const long long n_ = clock64(); tr_t[0] += n_ - tr_c; tr_c = n_; }
+          const uint8_t *buf = smem + Cfg::kExchOff + b * Cfg::kExchBytes;
+          float4 z[2];
+#pragma unroll
+          for (int g = 0; g < 2; ++g) z[g] = *reinterpret_cast<const float4 *>(buf + off_t[g]);
+#pragma unroll
+          for (int e = 0; e < kMixSlots; ++e) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (active & (1u << (g * kMixSlots + e))) {
+                const uint32_t off = (e & 1) ? (off_s[g][e >> 1] >> 16) : (off_s[g][e >> 1] & 0xffffu);
+                const float cf = csr_coef[e * kTileRows + rows[g]];
+                const float4 y = *reinterpret_cast<const float4 *>(buf + off);
+                z[g].x = fmaf(cf, y.x, z[g].x);
+                z[g].y = fmaf(cf, y.y, z[g].y);
+                z[g].z = fmaf(cf, y.z, z[g].z);
+                z[g].w = fmaf(cf, y.w, z[g].w);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&xempty[b]);  // planes consumed: the drain warps may refill them
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const long long tok = tok0 + rows[g];
+            if (rows[g] < a.tile_tokens && tok < a.n_tokens) {
+              const float x0 = fmaxf(z[g].x, 0.f), x1 = fmaxf(z[g].y, 0.f), x2 = fmaxf(z[g].z, 0.f), x3 = fmaxf(z[g].w, 0.f);
+              const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
+              const uint32_t l0 = pack_bf16x2(x0 - bf16_lo_as_float(h0), x1 - bf16_hi_as_float(h0));
+              const uint32_t l1 = pack_bf16x2(x2 - bf16_lo_as_float(h1), x3 - bf16_hi_as_float(h1));
+              *reinterpret_cast<uint2 *>(a.epi.y_hi + tok * a.epi.cs_out + c0) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(a.epi.y_lo + tok * a.epi.cs_out + c0) = make_uint2(l0, l1);
+            }
+          }
+          if (tr) { const long long n_ = clock64(); tr_t[1] += n_ - tr_c; tr_c = n_; }
+        }
+      }
+    }
+    if (tr) {
+      a.trace[8] = tr_t[0];
+      a.trace[9] = tr_t[1];
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -133,8 +133,9 @@ int cosk_profile_read(cosk_model *m, int32_t kind, int32_t block, double *ms, in
 int cosk_device_error(cosk_model *m, uint32_t *code);
 
 /* Phase timers (SM clock cycles, CTA 0) of the last graph-conv launch when the handle was created with
- * COSK_TRACE=1 in the environment: [0..6] epilogue set 0 {wait acc, tmem ld, exchange, gather, store,
- * total, items}, [8..14] set 1, [16..18] MMA thread {wait acc free, wait operands, total}.  Debug aid. */
+ * COSK_TRACE=1 in the environment: [0..3] drain warp {wait accumulator, tmem load + fold, wait exchange
+ * buffer, write planes}, [5] drain total, [6] work items, [8..9] mix warp {wait planes, gather + store},
+ * [16..18] MMA thread {wait accumulator free, wait operands, total}.  Debug aid. */
 int cosk_trace_read(cosk_model *m, uint64_t *out, int32_t n);
 
 const char *cosk_last_error(const cosk_model *m);
