@@ -34,9 +34,10 @@ ALGO = {
     "cost_gcn_mod": {"state": 3.072e6, "io": 600 + 240 + 2048, "flops": 318.0e6, "warm": 300, "period": 1},
 }
 NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*"}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams, from the `ncu --set full` captures
-# summarised in profiles/ (r1e_ncu_full_summary.csv); None where no capture exists for the kernel.
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches
+# listed in profiles/r1h_dram_bytes_per_launch.csv (ncu, --cache-control none); None where no capture exists.
+NCU_TRAFFIC = {"tcn<64>": 565.0e6, "tcn<128>": 1136.0e6, "tcn<256>": 2322.0e6, "gcn<64>": 68.0e6, "gcn<128>": 146.0e6,
+               "gcn<256>": 300.0e6}
 
 
 def load_peaks():
@@ -294,7 +295,7 @@ def run_ours(args, rank, world, local_rank):
     k_tf_credit = 2.0 * k_macs / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
     issued_k = (9 * cout + res_k) if kname == "tcn" else 4 * cin
     k_tf_issued = 3 * 2.0 * (tokens * 128.0 / 125.0) * cout * issued_k / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>")
+    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 else None
     step_bytes = algo["state"] + algo["io"]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -68,6 +68,7 @@ struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
   int gcn_identity_mma = 1;  // identity gcn_residual as a 4th GEMM column group (COSK_GCN_IDENTITY_MMA=0: add input rows instead)
+  int tcn_reverse = 1;  // temporal convs walk tiles last-to-first so producer->consumer hand-offs hit L2 (COSK_TCN_REVERSE=0 disables)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
@@ -491,6 +492,7 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
     a.kb_res = bc.res_kind == COSK_RES_CONV ? bc.cin / kBK : 0;
     a.n_tiles = m->n_tiles;
     a.tile_tokens = m->tile_tokens;
+    a.reverse = m->tcn_reverse;
     a.n_tokens = m->n_tokens;
     a.epi.bias = b.d_tcn_b;
     a.epi.r_hi = bc.res_kind == COSK_RES_IDENTITY ? in.hi(res_slot) : nullptr;
@@ -660,6 +662,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_TCN_REVERSE")) m->tcn_reverse = atoi(e);
   if (const char *e = getenv("COSK_GCN_IDENTITY_MMA")) m->gcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_TRACE")) {
     if (atoi(e) && cudaMalloc(&m->d_trace, 64 * sizeof(unsigned long long)) == cudaSuccess)

@@ -132,6 +132,8 @@ struct TcTcnArgs {
   int kb_per_tap;       // C / 64
   int kb_res;           // Cr / 64 when res_kind == 2 else 0
   int n_tiles, tile_tokens;
+  int reverse;  // 1: walk the tiles from the last to the first (the producer kernel wrote them first to last, so the
+                // most recently written rows -- the ones still in L2 -- are consumed first)
   long long n_tokens;
   EpiArgs epi;
   unsigned int *dbg;
@@ -206,7 +208,8 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
     if (lane == 0) {
       PipeState pa, pb;
       bool ok = true;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+      for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x) {
+        const int tile = a.reverse ? a.n_tiles - 1 - ti : ti;
         const int tok0 = tile * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
@@ -272,7 +275,8 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
-    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x, ++it) {
+      const int tile = a.reverse ? a.n_tiles - 1 - ti : ti;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
@@ -386,7 +390,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
     if (lane == 0) {
       PipeState pa, pb;
       bool ok = true;
-      for (int pr = cluster_id; ok && pr < n_pairs; pr += n_clusters) {
+      for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters) {
+        const int pr = a.reverse ? n_pairs - 1 - pi : pi;
         const int tok0 = (2 * pr + (int)rank) * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
@@ -452,7 +457,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
-    for (int pr = cluster_id; ok && pr < n_pairs; pr += n_clusters, ++it) {
+    for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters, ++it) {
+      const int pr = a.reverse ? n_pairs - 1 - pi : pi;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;

@@ -192,3 +192,62 @@ def test_long_run_pool_window_exact():
     # constant after pool_size further emissions and logits stop changing bit for bit
     assert len(outs) > 150
     assert torch.equal(outs[-1], outs[-2]) and torch.equal(outs[-1], outs[-40])
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+def test_kinetics_skeleton_stack(path):
+    """V = 18 (OpenPose) graph, 7 skeletons = 126 token rows per tile, a strided 3-block stack with every
+    residual kind: emitted outputs equal the oracle's clip math; odd stream counts leave a ragged last tile."""
+    blocks = [weights.BlockSpec(64, 64, 1, False), weights.BlockSpec(64, 64, 1, True), weights.BlockSpec(64, 128, 2, True)]
+    arch = ArchSpec(blocks, padding=4, skeleton="kinetics", head=False, block_names=["0.", "1.", "2."])
+    sd = weights.make_state_dict(arch, seed=31, randomize=True)
+    B, T = 23, 30  # 23 skeletons -> 4 tiles, the last one partly filled
+    x = weights.make_input((B, 64, T, 18), seed=32)
+    with torch.no_grad():
+        target = regular.stack_features(x, sd, arch)
+    stack = cs.CoStack([cs.BlockSpec(b.cin, b.cout, b.stride, b.residual) for b in blocks], padding=4, skeleton="kinetics",
+                       kernel_path=path)
+    mapped = {}
+    for k, v in sd.items():
+        i, rest = k.split(".", 1)
+        spec = blocks[int(i)]
+        if spec.res_kind == 0:
+            mapped[f"{i}.{rest}"] = v
+        elif rest.startswith("residual"):
+            mapped[f"{i}.0.0.{rest}"] = v
+        else:
+            mapped[f"{i}.0.1.{rest}"] = v
+    stack.load_state_dict(mapped, strict=True)
+    out = stack.forward_steps(x.to(DEV))
+    assert stack.device_error() == 0
+    out = out.cpu()
+    n = out.shape[2]
+    assert n == target.shape[2] - arch.stack_padding // arch.stack_stride
+    assert _rel_err(out, target[:, :, :n]) < 2e-4
+    if path == "auto":
+        assert stack.tensor_core_blocks() == [3, 3, 3]
+
+
+def test_single_stream_and_step_vs_steps():
+    """N = 1 (one partly filled tile): step-by-step emissions equal forward_steps bit for bit, and the
+    logits match the oracle."""
+    arch, sd, m = _load_model(cs.CoStGcnMod, weights.cost_gcn_mod_arch, False)
+    x = weights.make_input((1, 3, 302, 25, 2), seed=15)
+    xd = x.to(DEV)
+    outs = []
+    for t in range(x.shape[2]):
+        o = m.forward_step(xd[:, :, t].contiguous())
+        if o is not None:
+            outs.append(o.clone())
+    assert len(outs) == 3  # frames 299, 300, 301
+    m.clean_state()
+    ys = m.forward_steps(xd)
+    assert tuple(ys.shape) == (1, 60, 3)
+    for j, o in enumerate(outs):
+        assert torch.equal(ys[:, :, j], o)
+    ref = step.StepModel(sd, arch)
+    with torch.no_grad():
+        want = ref.forward_steps(x)
+    assert float((ys.cpu() - want).abs().max()) <= 1e-3
+    assert torch.equal(ys.cpu().argmax(1), want.argmax(1))
+    assert m.device_error() == 0

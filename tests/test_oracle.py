@@ -156,3 +156,16 @@ def test_regular_model_vs_golden(golden):
             ref = torch.from_numpy(g[f"{tag}_block{li + 1}_mid_rnd"])
             got = y[0, :, y.shape[2] // 2]
             assert torch.allclose(got, ref, atol=1e-5 * max(1.0, float(ref.abs().max()))), li
+
+
+def test_step_oracle_kinetics_graph():
+    """The step oracle on the 18-joint Kinetics graph (strided conv-residual block): prefix relation."""
+    arch = ArchSpec([BlockSpec(4, 4, 1, False), BlockSpec(4, 8, 2)], padding=4, skeleton="kinetics", head=False,
+                    block_names=["0.", "1."])
+    sd = weights.make_state_dict(arch, seed=41, randomize=True)
+    x = weights.make_input((2, 4, 30, 18), seed=42)
+    target = regular.stack_features(x, sd, arch)
+    out = step.StepModel(sd, arch).forward_steps(x)
+    n = out.shape[2]
+    assert n == target.shape[2] - arch.stack_padding // arch.stack_stride
+    assert torch.allclose(out, target[:, :, :n], atol=1e-6)
