@@ -542,6 +542,16 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
   return COSK_OK;
 }
 
+// ---- the integer schedule (shared by the device path and cosk_simulate_schedule) -------------------
+// co.Conv2d step semantics: the n-th input (0-based) of a 9-tap temporal conv with padding p and
+// stride s produces an output iff n >= 8 - p and (n - (8 - p)) % s == 0   (SURVEY.md section 3.3).
+inline bool tcn_fires(long long n, int padding, int stride) {
+  const int first = (kTaps - 1) - padding;
+  return n >= first && (n - first) % stride == 0;
+}
+// co.AvgPool1d(P, stride 1, padding pp): the m-th pooled vector yields logits iff m >= P - 1 - pp.
+inline bool head_fires(long long m_, int pool_size, int pool_padding) { return m_ >= (long long)pool_size - 1 - pool_padding; }
+
 int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s) {
   const cosk_config &c = m->cfg;
   int rc;
@@ -559,7 +569,6 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   }
   const ActBuf *in = &m->xin;
   bool alive = true;
-  const int first = (kTaps - 1) - c.padding;
   for (int i = 0; i < c.n_blocks; ++i) {
     m->last_flags[i] = 0;
     if (!alive) continue;
@@ -568,7 +577,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const long long n = b.n_in;  // index of this input == index of the predecessor's emission
     const int in_slot = (int)(n % kOutSlots);
     if ((rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) return rc;
-    const bool fire = n >= first && (n - first) % bc.stride == 0;
+    const bool fire = tcn_fires(n, c.padding, bc.stride);
     if (fire) {
       const int res_slot = (int)((n - kResDelay) % kOutSlots);  // n >= first >= 4
       if ((rc = run_tcn(m, i, *in, res_slot, n, (int)(b.n_out % kOutSlots), s))) return rc;
@@ -584,7 +593,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const BlockW &last = m->blk[c.n_blocks - 1];
     const int slot = (int)((last.n_out - 1) % kOutSlots);
     if (c.classes > 0) {
-      emit = m->pool_n >= (long long)c.pool_size - 1 - c.pool_padding ? 1 : 0;
+      emit = head_fires(m->pool_n, c.pool_size, c.pool_padding) ? 1 : 0;
       if ((rc = prof_mark(m, 3, -1, s))) return rc;
       HeadArgs h;
       h.y_hi = last.out.hi(slot);
@@ -603,7 +612,8 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
       h.b = m->d_fc_b;
       h.classes = c.classes;
       h.out = out;
-      CK(launch_k(m, k_head, dim3((unsigned)m->n_streams), dim3(256), (2 * last.out.cs + last.out.c) * sizeof(float), s, h));
+      CK(launch_k(m, k_head, dim3((unsigned)((m->n_streams + kHeadStreams - 1) / kHeadStreams)), dim3(256 * kHeadStreams),
+                  (size_t)kHeadStreams * (2 * last.out.cs + last.out.c) * sizeof(float), s, h));
       m->launches++;
       m->pool_n++;
     } else {
@@ -864,6 +874,30 @@ int cosk_device_error(cosk_model *m, uint32_t *code) {
   unsigned int h[4] = {0, 0, 0, 0};
   CK(cudaMemcpy(h, m->d_dbg, sizeof h, cudaMemcpyDeviceToHost));
   *code = h[0];
+  return COSK_OK;
+}
+
+int cosk_simulate_schedule(const cosk_config *cfg, int32_t T, int32_t *flags) {
+  if (!cfg || !flags || T < 0 || cfg->n_blocks < 1 || cfg->n_blocks > COSK_MAX_BLOCKS) return COSK_ERR_ARG;
+  long long n_in[COSK_MAX_BLOCKS] = {0}, pool_n = 0;
+  const int w = cfg->n_blocks + 1;
+  for (int t = 0; t < T; ++t) {
+    bool alive = true;
+    for (int i = 0; i < cfg->n_blocks; ++i) {
+      flags[t * w + i] = 0;
+      if (!alive) continue;
+      const bool fire = tcn_fires(n_in[i], cfg->padding, cfg->blocks[i].stride);
+      n_in[i]++;
+      alive = fire;
+      flags[t * w + i] = fire ? 1 : 0;
+    }
+    int emit = 0;
+    if (alive) {
+      if (cfg->classes > 0) emit = head_fires(pool_n++, cfg->pool_size, cfg->pool_padding) ? 1 : 0;
+      else emit = 1;
+    }
+    flags[t * w + cfg->n_blocks] = emit;
+  }
   return COSK_OK;
 }
 

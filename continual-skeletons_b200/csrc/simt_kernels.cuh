@@ -193,7 +193,7 @@ constexpr int kSmallKMax = 32;
 
 __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
   __shared__ float xs[kTileRows][8 + 1];             // normalised input rows
-  __shared__ float xa[kTileRows][kSmallKMax + 1];    // [part-major mixed inputs | raw input]
+  __shared__ __align__(16) float xa[kSmallKMax][kTileRows + 4];  // k-major [part-major mixed inputs | raw input]
   extern __shared__ __align__(16) float w_s[];       // [K][cout] k-major weights, then bias[cout]
   const int K = (3 + a.res_conv) * a.cin;
   const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kTileRows * K; i += blockDim.x) {
-    const int r = i / K, k = i - r * K;
+    const int k = i / kTileRows, r = i - k * kTileRows;
     const int part = k / a.cin, c = k - part * a.cin;
     float v = 0.f;
     if (r < rows_valid) {
@@ -224,42 +224,43 @@ __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
         v = xs[r][c];
       }
     }
-    xa[r][k] = v;
+    xa[k][r] = v;
   }
   __syncthreads();
-  const int r = threadIdx.x >> 1;
-  if (r >= rows_valid) return;
-  const long long tok = tok0 + r;
-  for (int n0 = (threadIdx.x & 1) * 32; n0 < a.cout; n0 += 64) {
-    float acc[32];
+  // register tile: 4 token rows x 8 output channels per thread; 32 row groups x 8 channel groups per pass of 64 channels
+  const int rg = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  for (int n0 = cg * 8; n0 < a.cout; n0 += 64) {
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = bias_s[n0 + j];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = bias_s[n0 + j];
     for (int k = 0; k < K; ++k) {
-      const float xv = xa[r][k];
-      const float4 *wr = reinterpret_cast<const float4 *>(&w_s[k * a.cout + n0]);
+      const float4 xv = *reinterpret_cast<const float4 *>(&xa[k][rg * 4]);
+      const float4 w0 = *reinterpret_cast<const float4 *>(&w_s[k * a.cout + n0]);
+      const float4 w1 = *reinterpret_cast<const float4 *>(&w_s[k * a.cout + n0 + 4]);
+      const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+      const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 w4 = wr[j];
-        acc[4 * j] = fmaf(xv, w4.x, acc[4 * j]);
-        acc[4 * j + 1] = fmaf(xv, w4.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(xv, w4.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(xv, w4.w, acc[4 * j + 3]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wr[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      if (r >= rows_valid) continue;
+      const long long tok = tok0 + r;
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x0 = fmaxf(acc[i][2 * j], 0.f), x1 = fmaxf(acc[i][2 * j + 1], 0.f);
+        const uint32_t h = pack_bf16x2(x0, x1);
+        oh[j] = h;
+        ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
       }
-    }
-    uint32_t oh[16], ol[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float x0 = fmaxf(acc[2 * j], 0.f), x1 = fmaxf(acc[2 * j + 1], 0.f);
-      const uint32_t h = pack_bf16x2(x0, x1);
-      oh[j] = h;
-      ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
-    }
-    uint4 *qh = reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + n0);
-    uint4 *ql = reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + n0);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      qh[g] = make_uint4(oh[4 * g], oh[4 * g + 1], oh[4 * g + 2], oh[4 * g + 3]);
-      ql[g] = make_uint4(ol[4 * g], ol[4 * g + 1], ol[4 * g + 2], ol[4 * g + 3]);
+      *reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + n0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      *reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + n0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
     }
   }
 }
@@ -351,53 +352,72 @@ struct HeadArgs {
   float *out;  // [N][classes]
 };
 
-__global__ void __launch_bounds__(256) k_head(HeadArgs a) {
+constexpr int kHeadStreams = 4;  // streams per CTA (256 threads each): the FC weight rows are fetched once for all of them
+
+__global__ void __launch_bounds__(256 * kHeadStreams) k_head(HeadArgs a) {
   extern __shared__ float head_s[];
   pdl_trigger();
   pdl_wait();
-  float *part = head_s;             // [2][cs] per-thread-half partial spatial means
-  float *mean_s = head_s + 2 * a.cs;  // [c] window mean
-  const long long n = blockIdx.x;
-  const long long tok0 = n * a.S * a.V;
-  const int half = threadIdx.x >> 7, t128 = threadIdx.x & 127;
-  // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
-  for (int cp = t128; cp < a.cs / 2; cp += 128) {
-    float t0 = 0.f, t1 = 0.f;
-    for (int s = half; s < a.S; s += 2) {
-      float p0 = 0.f, p1 = 0.f;
-      const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
+  const int g = threadIdx.x >> 8, tid = threadIdx.x & 255;
+  float *part = head_s + g * 2 * a.cs;                    // [streams][2][cs] partial spatial means
+  float *mean_s = head_s + kHeadStreams * 2 * a.cs;       // [streams][c] window means
+  const long long n0 = (long long)blockIdx.x * kHeadStreams;
+  const long long n = n0 + g;
+  const bool live = n < a.n_streams;
+  const int half = tid >> 7, t128 = tid & 127;
+  if (live) {
+    const long long tok0 = n * a.S * a.V;
+    // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
+    for (int cp = t128; cp < a.cs / 2; cp += 128) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int s = half; s < a.S; s += 2) {
+        float p0 = 0.f, p1 = 0.f;
+        const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
 #pragma unroll 5
-      for (int v = 0; v < a.V; ++v) {
-        const uint32_t h = *reinterpret_cast<const uint32_t *>(a.y_hi + base + (long long)v * a.cs);
-        const uint32_t l = *reinterpret_cast<const uint32_t *>(a.y_lo + base + (long long)v * a.cs);
-        p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
-        p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
+        for (int v = 0; v < a.V; ++v) {
+          const uint32_t h = *reinterpret_cast<const uint32_t *>(a.y_hi + base + (long long)v * a.cs);
+          const uint32_t l = *reinterpret_cast<const uint32_t *>(a.y_lo + base + (long long)v * a.cs);
+          p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
+          p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
+        }
+        t0 += p0 / (float)a.V;
+        t1 += p1 / (float)a.V;
       }
-      t0 += p0 / (float)a.V;
-      t1 += p1 / (float)a.V;
+      part[half * a.cs + 2 * cp] = t0;
+      part[half * a.cs + 2 * cp + 1] = t1;
     }
-    part[half * a.cs + 2 * cp] = t0;
-    part[half * a.cs + 2 * cp + 1] = t1;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < a.c; c += blockDim.x) {
-    const float h = (part[c] + part[a.cs + c]) / (float)a.S;
-    const long long ri = ((long long)a.slot * a.n_streams + n) * a.c + c;
-    const float old = a.ring[ri];
-    a.ring[ri] = h;
-    const double s2 = a.sum[n * a.c + c] + ((double)h - (double)old);
-    a.sum[n * a.c + c] = s2;
-    mean_s[c] = (float)(s2 / (double)a.P);
+  if (live) {
+    for (int c = tid; c < a.c; c += 256) {
+      const float h = (part[c] + part[a.cs + c]) / (float)a.S;
+      const long long ri = ((long long)a.slot * a.n_streams + n) * a.c + c;
+      const float old = a.ring[ri];
+      a.ring[ri] = h;
+      const double s2 = a.sum[n * a.c + c] + ((double)h - (double)old);
+      a.sum[n * a.c + c] = s2;
+      mean_s[g * a.c + c] = (float)(s2 / (double)a.P);
+    }
   }
   if (!a.emit) return;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int k = warp; k < a.classes; k += nw) {
-    float p = 0.f;
-    for (int c = lane; c < a.c; c += 32) p = fmaf(a.w[(long long)k * a.c + c], mean_s[c], p);
+    float p[kHeadStreams];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    if (lane == 0) a.out[n * a.classes + k] = p + a.b[k];
+    for (int j = 0; j < kHeadStreams; ++j) p[j] = 0.f;
+    for (int c = lane; c < a.c; c += 32) {
+      const float wv = a.w[(long long)k * a.c + c];
+#pragma unroll
+      for (int j = 0; j < kHeadStreams; ++j) p[j] = fmaf(wv, mean_s[j * a.c + c], p[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kHeadStreams; ++j) {
+      float v = p[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && n0 + j < a.n_streams) a.out[(n0 + j) * a.classes + k] = v + a.b[k];
+    }
   }
 }
 

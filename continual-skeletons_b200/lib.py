@@ -80,6 +80,7 @@ SYMBOLS = {
     "cosk_steps": (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _P]),
     "cosk_state_bytes": (ctypes.c_int64, [_P]),
     "cosk_last_schedule": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
+    "cosk_simulate_schedule": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "cosk_frame_count": (ctypes.c_int64, [_P]),
     "cosk_read_block": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P]),
     "cosk_launch_count": (ctypes.c_int64, [_P]),

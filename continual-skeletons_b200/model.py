@@ -189,18 +189,8 @@ class _Engine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise CoskError(f"continual_skeletons_b200 runs on CUDA devices only, got {self.device}")
-        cfg = _lib.Config()
-        cfg.abi_version = _lib.ABI_VERSION
-        cfg.vertices, cfg.persons, cfg.c_in = owner._V, owner._S, owner._c_in
-        cfg.n_blocks, cfg.padding = len(owner._specs), owner._pad
-        cfg.classes = owner._classes if owner._head else 0
-        cfg.pool_size, cfg.pool_padding = (owner.pool_size, owner.pool_padding) if owner._head else (0, 0)
-        cfg.data_bn = 1 if owner._head else 0
+        cfg = owner._config()
         cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        cfg.path = {"auto": 0, "simt": 1}[owner._path]
-        for i, sp in enumerate(owner._specs):
-            cfg.blocks[i].cin, cfg.blocks[i].cout = sp.cin, sp.cout
-            cfg.blocks[i].stride, cfg.blocks[i].res_kind = sp.stride, sp.res_kind
         h = ctypes.c_void_p()
         rc = self.lib.cosk_create(ctypes.byref(cfg), ctypes.byref(h))
         if rc != 0:
@@ -245,6 +235,33 @@ class _CoBase(nn.Module):
             cum *= sp.stride
         self.receptive_field, self.stride, self.padding = rf, cum, p
         self.delay = rf - 1 - p
+
+    def _config(self):
+        """The cosk_config of this stack (include/cosk.h)."""
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.vertices, cfg.persons, cfg.c_in = self._V, self._S, self._c_in
+        cfg.n_blocks, cfg.padding = len(self._specs), self._pad
+        cfg.classes = self._classes if self._head else 0
+        cfg.pool_size, cfg.pool_padding = (self.pool_size, self.pool_padding) if self._head else (0, 0)
+        cfg.data_bn = 1 if self._head else 0
+        cfg.path = {"auto": 0, "simt": 1}[self._path]
+        for i, sp in enumerate(self._specs):
+            cfg.blocks[i].cin, cfg.blocks[i].cout = sp.cin, sp.cout
+            cfg.blocks[i].stride, cfg.blocks[i].res_kind = sp.stride, sp.res_kind
+        return cfg
+
+    def simulate_schedule(self, frames):
+        """Emission flags (one per block + head) of ``frames`` consecutive steps from a fresh state, computed
+        by the library's host-side bookkeeping without a GPU."""
+        lib = _lib.load_library()
+        cfg = self._config()
+        w = len(self._specs) + 1
+        buf = (ctypes.c_int32 * (frames * w))()
+        rc = lib.cosk_simulate_schedule(ctypes.byref(cfg), frames, buf)
+        if rc != 0:
+            raise CoskError(f"cosk_simulate_schedule failed ({rc})")
+        return [tuple(bool(buf[t * w + i]) for i in range(w)) for t in range(frames)]
 
     # -- weights ------------------------------------------------------------------------------
     def _block_modules(self):

@@ -112,6 +112,9 @@ int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int
 int64_t cosk_state_bytes(const cosk_model *m);
 /* flags[i] = 1 iff block i emitted during the last cosk_step; flags[n_blocks] = head emitted. */
 int cosk_last_schedule(const cosk_model *m, int32_t *flags, int32_t n);
+/* Host-only: the emission schedule of T consecutive frames from a fresh state, without touching a device
+ * (same integer bookkeeping cosk_step uses).  flags is [T][n_blocks + 1], laid out like cosk_last_schedule. */
+int cosk_simulate_schedule(const cosk_config *cfg, int32_t T, int32_t *flags);
 /* frames pushed since the last reset */
 int64_t cosk_frame_count(const cosk_model *m);
 /* last emitted output of block i as fp32 (N*S, cout, V) into dst_dev (debug / feature taps) */

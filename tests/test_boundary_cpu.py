@@ -151,3 +151,39 @@ def test_unsupported_arguments():
         m.forward_steps(torch.rand(1, 3, 4, 25, 2), pad_end=True)
     with pytest.raises(NotImplementedError):
         m.forward_step(torch.rand(1, 3, 25, 2), update_state=False)
+
+
+@pytest.mark.parametrize("cls,arch_fn", [(cs.CoStGcn, weights.cost_gcn_arch), (cs.CoStGcnMod, weights.cost_gcn_mod_arch)])
+def test_host_schedule_bit_exact_vs_step_oracle(cls, arch_fn):
+    """The library's integer bookkeeping (which block fires on which frame, when logits are due),
+    run on the host without a GPU, equals the step oracle's trace for 320 frames."""
+    from oracle import step
+
+    arch = arch_fn()
+    sd = weights.make_state_dict(arch, seed=3)
+    ref = step.StepModel(sd, arch)
+    T = 320
+    x = torch.zeros(1, 3, 25, 2)
+    with torch.no_grad():
+        for _ in range(T):
+            ref.forward_step(x)
+    got = cls().simulate_schedule(T)
+    assert got == [tuple(f) for f in ref.trace]
+    first = [t for t, f in enumerate(got) if f[-1]][0]
+    assert first == (296 if cls is cs.CoStGcn else 299)
+
+
+def test_host_schedule_of_a_strided_stack():
+    from oracle import step
+
+    blocks = [weights.BlockSpec(3, 4, 2, True), weights.BlockSpec(4, 4, 1, True), weights.BlockSpec(4, 8, 2, True)]
+    for pad in (4, 0):
+        arch = ArchSpec(blocks, padding=pad, head=False, block_names=["0.", "1.", "2."])
+        sd = weights.make_state_dict(arch, seed=5)
+        ref = step.StepModel(sd, arch)
+        x = torch.zeros(1, 3, 25)
+        with torch.no_grad():
+            for _ in range(60):
+                ref.forward_step(x)
+        stack = cs.CoStack([cs.BlockSpec(b.cin, b.cout, b.stride, b.residual) for b in blocks], padding=pad)
+        assert stack.simulate_schedule(60) == [tuple(f) for f in ref.trace]
