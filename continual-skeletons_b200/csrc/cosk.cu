@@ -69,6 +69,7 @@ struct cosk_model {
   int num_sms = 148;
   int gcn_identity_mma = 1;  // identity gcn_residual as a 4th GEMM column group (COSK_GCN_IDENTITY_MMA=0: add input rows instead)
   int tcn_reverse = 1;  // temporal convs walk tiles last-to-first so producer->consumer hand-offs hit L2 (COSK_TCN_REVERSE=0 disables)
+  int gcn_single_stage = 1;  // cin = 64 graph convs: 1 operand stage + 4 exchange buffers (COSK_GCN_SINGLE_STAGE=0: 2 stages + 1 buffer)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
@@ -387,11 +388,11 @@ int launch_tc_tcn2(cosk_model *m, const TcTcnArgs &args, cudaStream_t s) {
   CK(launch_k(m, k_tc_tcn2<COUT>, dim3(grid), dim3(256), TcTcn2Cfg<COUT>::kSmemBytes, s, args));
   return COSK_OK;
 }
-template <int P>
+template <int P, int STAGES>
 int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  if (m->d_trace) CK(launch_k(m, k_tc_gcn<P, true>, dim3(grid), dim3(512), TcGcnCfg<P>::kSmemBytes, s, args));
-  else CK(launch_k(m, k_tc_gcn<P, false>, dim3(grid), dim3(512), TcGcnCfg<P>::kSmemBytes, s, args));
+  if (m->d_trace) CK(launch_k(m, k_tc_gcn<P, STAGES, true>, dim3(grid), dim3(512), TcGcnCfg<P, STAGES>::kSmemBytes, s, args));
+  else CK(launch_k(m, k_tc_gcn<P, STAGES, false>, dim3(grid), dim3(512), TcGcnCfg<P, STAGES>::kSmemBytes, s, args));
   return COSK_OK;
 }
 
@@ -402,10 +403,14 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_tcn2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcn2Cfg<256>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
-  CK(cudaFuncSetAttribute(k_tc_gcn<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<3, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<3, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
   return COSK_OK;
 }
 
@@ -439,7 +444,10 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.epi.y_lo = b.ring.lo(ring_slot);
     a.epi.cs_out = b.ring.cs;
     a.dbg = m->d_dbg;
-    rc = b.gcn_parts == 4 ? launch_tc_gcn<4>(m, a, s) : launch_tc_gcn<3>(m, a, s);
+    // one K-block per work item (cin = 64): single operand stage, four exchange buffers
+    const bool one_kb = bc.cin == kBK && m->gcn_single_stage;
+    if (b.gcn_parts == 4) rc = one_kb ? launch_tc_gcn<4, 1>(m, a, s) : launch_tc_gcn<4, 2>(m, a, s);
+    else rc = one_kb ? launch_tc_gcn<3, 1>(m, a, s) : launch_tc_gcn<3, 2>(m, a, s);
     if (rc) return rc;
   } else {
     GcnArgs a;
@@ -672,6 +680,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_GCN_SINGLE_STAGE")) m->gcn_single_stage = atoi(e);
   if (const char *e = getenv("COSK_TCN_REVERSE")) m->tcn_reverse = atoi(e);
   if (const char *e = getenv("COSK_GCN_IDENTITY_MMA")) m->gcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_TRACE")) {

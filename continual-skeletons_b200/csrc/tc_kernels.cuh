@@ -515,24 +515,29 @@ struct TcGcnArgs {
   unsigned int *dbg;
 };
 
-template <int P>
+template <int P, int STAGES>
 struct TcGcnCfg {
+  // STAGES = 2: operand ring two K-blocks deep (cin >= 128: several K-blocks per work item).
+  // STAGES = 1: a single operand stage -- enough when a work item is one K-block (cin = 64), because the
+  //             next item's load + MMA fit inside the current item's epilogue -- and the shared memory
+  //             saved buys four exchange buffers, so drain and mix warps run fully decoupled.
   static constexpr int kN = P * 64;
   static constexpr int kBBytes = kN * kBK * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kStages = 2;
+  static constexpr int kStages = STAGES;
   static constexpr int kPlaneBytes = kTileRows * kGcnChunk * 4;  // 8 KB: 128 rows x 16 floats
   static constexpr int kExchBytes = 3 * kPlaneBytes;             // planes T, Y1, Y2
-  static constexpr int kExchBufs = P == 3 ? 2 : 1;
+  static constexpr int kExchBufs = STAGES == 1 ? 4 : (P == 3 ? 2 : 1);
   static constexpr int kExchOff = kStages * kStageBytes;
-  static constexpr int kCsrOff = kExchOff + kExchBufs * kExchBytes;  // per row: n, src[8] (bytes), coef[8]
-  static constexpr int kCsrBytes = kTileRows * (4 + 4 * kMixSlots) + kTileRows * 8;  // n, coef, src (+ row order)
+  static constexpr int kCsrOff = kExchOff + kExchBufs * kExchBytes;  // per row: n, coef[slots], src[slots], row order
+  static constexpr int kCsrBytes = kTileRows * (4 + 4 * kMixSlots) + kTileRows * 8;
   static constexpr int kBarOff = kCsrOff + kCsrBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + 256 * 4 + 1024;
   static constexpr int kAccStride = 256;
   static constexpr int kTmemCols = 512;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+  static_assert(kExchBufs <= 4, "exchange barriers");
 };
 
 // byte offset of element (row, col) in an exchange plane: 64-byte rows, 16-byte chunks XOR-swizzled with
@@ -540,9 +545,37 @@ struct TcGcnCfg {
 // reading whole rows, never meet in a bank
 __device__ __forceinline__ uint32_t exch_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 
-template <int P, bool TRACE>
+// Mix-phase gather of one 16-channel chunk for the two row groups of a lane, with the slot count N known
+// at compile time: all shared-memory loads are issued before the first FMA (no branch per slot), unused
+// slots of a row carry a zero coefficient and offset 0.
+template <int N>
+__device__ __forceinline__ void mix_gather(const uint8_t *buf, const uint32_t (&off_t)[2], const uint32_t (&off_s)[2][kMixSlots / 2],
+                                           const float (&cf)[2][kMixSlots], float4 (&z)[2]) {
+  float4 y[2][N > 0 ? N : 1];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    z[g] = *reinterpret_cast<const float4 *>(buf + off_t[g]);
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      const uint32_t off = (e & 1) ? (off_s[g][e >> 1] >> 16) : (off_s[g][e >> 1] & 0xffffu);
+      y[g][e] = *reinterpret_cast<const float4 *>(buf + off);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < N; ++e) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      z[g].x = fmaf(cf[g][e], y[g][e].x, z[g].x);
+      z[g].y = fmaf(cf[g][e], y[g][e].y, z[g].y);
+      z[g].z = fmaf(cf[g][e], y[g][e].z, z[g].z);
+      z[g].w = fmaf(cf[g][e], y[g][e].w, z[g].w);
+    }
+  }
+}
+
+template <int P, int STAGES, bool TRACE>
 __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
-  using Cfg = TcGcnCfg<P>;
+  using Cfg = TcGcnCfg<P, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
@@ -550,8 +583,8 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
   uint64_t *tfull = empty + Cfg::kStages;
   uint64_t *tempty = tfull + 2;
   uint64_t *xfull = tempty + 2;
-  uint64_t *xempty = xfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xempty + 2);
+  uint64_t *xempty = xfull + 4;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xempty + 4);
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
   // CSR of partitions 1 and 2 per tile row, shared by the mix warps
   int *csr_n = reinterpret_cast<int *>(smem + Cfg::kCsrOff);                 // [128]
@@ -570,6 +603,8 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull[s], 1);
       ptx::mbar_init(&tempty[s], 4);  // the four drain warps
+    }
+    for (int s = 0; s < Cfg::kExchBufs; ++s) {
       ptx::mbar_init(&xfull[s], 4);   // the four drain warps
       ptx::mbar_init(&xempty[s], 8);  // the eight mix warps
     }
@@ -761,8 +796,8 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
 #pragma unroll
           for (int j = 0; j < 16; ++j) t[j] = fmaf(d0, __uint_as_float(y0[j]), t[j]);
           if (tr) { const long long n_ = clock64(); tr_t[1] += n_ - tr_c; tr_c = n_; }
-          const uint32_t b = Cfg::kExchBufs == 2 ? (xc & 1) : 0;
-          const uint32_t use = Cfg::kExchBufs == 2 ? (xc >> 1) : xc;
+          const uint32_t b = xc % Cfg::kExchBufs;
+          const uint32_t use = xc / Cfg::kExchBufs;
           ok = ptx::mbar_wait(&xempty[b], (use & 1) ^ 1, a.dbg, kDbgEpiExchEmpty | (xc & 0xffff));
           if (!ok) break;
           if (tr) { const long long n_ = clock64(); tr_t[2] += n_ - tr_c; tr_c = n_; }
@@ -798,13 +833,15 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
     const int rr = lane >> 2, cq = lane & 3;
     int rows[2];
     uint32_t off_t[2], off_s[2][kMixSlots / 2];
-    uint32_t active = 0;
+    float cf[2][kMixSlots];
+    int nmax = 0;  // most slots any of this warp's 16 rows needs (warp-uniform; rows are count-sorted, so mostly 1-2)
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const int row = csr_perm[m * 16 + g * 8 + rr];
       rows[g] = row;
       off_t[g] = exch_off(row, cq);
       const int n = csr_n[row];
+      nmax = max(nmax, n);
 #pragma unroll
       for (int e = 0; e < kMixSlots; ++e) {
         const bool on = e < n;
@@ -812,9 +849,11 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
         const uint32_t off = on ? (1 + (sp >> 7)) * Cfg::kPlaneBytes + exch_off((int)(sp & 0x7f), cq) : 0u;
         if (e & 1) off_s[g][e >> 1] |= off << 16;
         else off_s[g][e >> 1] = off;
-        if (__any_sync(0xffffffffu, on)) active |= 1u << (g * kMixSlots + e);
+        cf[g][e] = on ? csr_coef[e * kTileRows + row] : 0.f;
       }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
     const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && m == 0 && lane == 0;
     unsigned long long tr_t[3] = {0, 0, 0};
     long long tr_c = 0;
@@ -826,30 +865,22 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++xc) {
           const int c0 = pass * 64 + c * kGcnChunk + 4 * cq;
-          const uint32_t b = Cfg::kExchBufs == 2 ? (xc & 1) : 0;
-          const uint32_t use = Cfg::kExchBufs == 2 ? (xc >> 1) : xc;
+          const uint32_t b = xc % Cfg::kExchBufs;
+          const uint32_t use = xc / Cfg::kExchBufs;
           if (tr) tr_c = clock64();
           ok = ptx::mbar_wait(&xfull[b], use & 1, a.dbg, kDbgEpiExchFull | (xc & 0xffff));
           if (!ok) break;
           if (tr) { const long long n_ = clock64(); tr_t[0] += n_ - tr_c; tr_c = n_; }
           const uint8_t *buf = smem + Cfg::kExchOff + b * Cfg::kExchBytes;
           float4 z[2];
-#pragma unroll
-          for (int g = 0; g < 2; ++g) z[g] = *reinterpret_cast<const float4 *>(buf + off_t[g]);
-#pragma unroll
-          for (int e = 0; e < kMixSlots; ++e) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (active & (1u << (g * kMixSlots + e))) {
-                const uint32_t off = (e & 1) ? (off_s[g][e >> 1] >> 16) : (off_s[g][e >> 1] & 0xffffu);
-                const float cf = csr_coef[e * kTileRows + rows[g]];
-                const float4 y = *reinterpret_cast<const float4 *>(buf + off);
-                z[g].x = fmaf(cf, y.x, z[g].x);
-                z[g].y = fmaf(cf, y.y, z[g].y);
-                z[g].z = fmaf(cf, y.z, z[g].z);
-                z[g].w = fmaf(cf, y.w, z[g].w);
-              }
-            }
+          switch (nmax) {
+            case 0: mix_gather<0>(buf, off_t, off_s, cf, z); break;
+            case 1: mix_gather<1>(buf, off_t, off_s, cf, z); break;
+            case 2: mix_gather<2>(buf, off_t, off_s, cf, z); break;
+            case 3: mix_gather<3>(buf, off_t, off_s, cf, z); break;
+            case 4: mix_gather<4>(buf, off_t, off_s, cf, z); break;
+            case 5: mix_gather<5>(buf, off_t, off_s, cf, z); break;
+            default: mix_gather<6>(buf, off_t, off_s, cf, z); break;
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&xempty[b]);  // planes consumed: the drain warps may refill them
