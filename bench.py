@@ -136,6 +136,14 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def kernel_label(path, kname, cout, kblock):
+    if path != "auto":
+        return f"k_{kname}_simt (layer {kblock + 1}, C={cout})"
+    if kname == "tcn":
+        return (f"k_tc_tcn<{cout}>" if cout == 64 else f"k_tc_tcn2<{cout}> (CTA pairs)") + f" (layer {kblock + 1})"
+    return f"k_tc_gcn<4> C={cout} (layer {kblock + 1})"
+
+
 def make_config(args, world):
     return {
         "workload": f"{NAMES[args.workload]} NTU RGB+D 60 joint stream, per-step forward_step, {args.streams} concurrent streams per GPU, "
@@ -308,7 +316,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "roofline": {
-            "bound": "hbm", "kernel": f"{'k_tc' if args.kernel_path == 'auto' else 'k'}_{kname}<{cout}> (layer {kblock + 1})",
+            "bound": "hbm", "kernel": kernel_label(args.kernel_path, kname, cout, kblock),
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
             "peak_source": peaks["source"],

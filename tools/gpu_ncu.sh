@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full capture (source-level) of selected kernels; usage: scripts_gpu_ncu.sh <kernel regex> <count> <out name>
+# ncu --set full capture (source-level) of selected kernels; usage: tools/gpu_ncu.sh <kernel regex> <count> <out name>
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 COSK_NCU=1 timeout 1500 ncu --profile-from-start off --set full --import-source on --clock-control none \
