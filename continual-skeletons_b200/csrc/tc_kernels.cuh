@@ -132,8 +132,9 @@ struct TcTcnArgs {
   int kb_per_tap;       // C / 64
   int kb_res;           // Cr / 64 when res_kind == 2 else 0
   int n_tiles, tile_tokens;
-  int reverse;  // 1: walk the tiles from the last to the first (the producer kernel wrote them first to last, so the
-                // most recently written rows -- the ones still in L2 -- are consumed first)
+  int reverse;  // 1: every CTA walks its own tiles (c, c + grid, ...) from the last to the first: the graph conv that
+                // produced the newest tap walked them first to last on the same CTA index (same SM / L2 partition),
+                // so the most recently written rows -- the ones still in L2 -- are consumed first
   long long n_tokens;
   EpiArgs epi;
   unsigned int *dbg;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
       PipeState pa, pb;
       bool ok = true;
       for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x) {
-        const int tile = a.reverse ? a.n_tiles - 1 - ti : ti;
+        const int tile = a.reverse ? (int)blockIdx.x + (int)gridDim.x * ((a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x) - (ti - (int)blockIdx.x) : ti;
         const int tok0 = tile * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
     bool ok = true;
     int it = 0;
     for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x, ++it) {
-      const int tile = a.reverse ? a.n_tiles - 1 - ti : ti;
+      const int tile = a.reverse ? (int)blockIdx.x + (int)gridDim.x * ((a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x) - (ti - (int)blockIdx.x) : ti;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
@@ -391,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
       PipeState pa, pb;
       bool ok = true;
       for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters) {
-        const int pr = a.reverse ? n_pairs - 1 - pi : pi;
+        const int pr = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
         const int tok0 = (2 * pr + (int)rank) * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
@@ -458,7 +459,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
     bool ok = true;
     int it = 0;
     for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters, ++it) {
-      const int pr = a.reverse ? n_pairs - 1 - pi : pi;
+      const int pr = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
