@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -53,8 +54,12 @@ struct BlockW {
   __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
   CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half;  // _half: box of cout/2 rows for the CTA-pair kernel
   bool tc_gcn = false, tc_tcn = false;
+  bool tcn_res_kblock = false;  // tensor-core temporal conv: the residual enters as extra K-blocks of the GEMM (folded
+                                // strided conv, or identity weights for the narrow layers) instead of epilogue loads
   long long n_in = 0, n_out = 0;
   ActBuf ring, out;
+  unsigned int *d_tile_cnt = nullptr;  // per-tile completion counters of this block's temporal conv (merged launches)
+  long long merge_ticket = 0;
 };
 
 struct ProfRec {
@@ -70,6 +75,12 @@ struct cosk_model {
   int gcn_identity_mma = 1;  // identity gcn_residual as a 4th GEMM column group (COSK_GCN_IDENTITY_MMA=0: add input rows instead)
   int tcn_reverse = 1;  // temporal convs walk tiles last-to-first so producer->consumer hand-offs hit L2 (COSK_TCN_REVERSE=0 disables)
   int gcn_single_stage = 1;  // cin = 64 graph convs: 1 operand stage + 4 exchange buffers (COSK_GCN_SINGLE_STAGE=0: 2 stages + 1 buffer)
+  int merge = 0;           // temporal conv of block L + graph conv of block L+1 in one cooperative launch (COSK_MERGE=1);
+                           // off: both roles turned out to be limited per SM, so splitting the SMs between them loses
+  int merge_min_tiles = 4 * 148;  // below this the two CTA groups are not worth splitting (COSK_MERGE_MIN_TILES)
+  int merge_split64 = 100;  // CTAs given to the temporal-conv role (64-channel layers)
+  int merge_split128 = 92;  // same for the 128-channel layers (CTA pairs)
+  int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
@@ -127,6 +138,7 @@ void free_state(cosk_model *m) {
   for (auto &b : m->blk) {
     dfree(b.ring.ptr);
     dfree(b.out.ptr);
+    dfree(b.d_tile_cnt);
   }
   dfree(m->d_pool_ring);
   dfree(m->d_pool_sum);
@@ -306,11 +318,19 @@ int prepare(cosk_model *m) {
       if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
     }
     if (b.tc_tcn) {
-      const int Kr = bc.res_kind == COSK_RES_CONV ? bc.cin : 0;
+      // The delayed residual x_{n-4} is streamed through the operand ring like a tenth tap: with the folded
+      // strided 1x1 conv as its weights (layers 5 and 8), or -- for the identity residual of the HBM-bound
+      // narrow layers -- with identity weights (exact under the split products), which removes every
+      // latency-bound load from the epilogue.  The 256-channel layers are tensor-bound and keep the add.
+      const bool ident_k = bc.res_kind == COSK_RES_IDENTITY && bc.cout <= 128 && m->tcn_identity_mma;
+      b.tcn_res_kblock = bc.res_kind == COSK_RES_CONV || ident_k;
+      const int Kr = b.tcn_res_kblock ? bc.cin : 0;
       std::vector<float> cat((size_t)bc.cout * (Kt + Kr));
       for (int r = 0; r < bc.cout; ++r) {
         memcpy(&cat[(size_t)r * (Kt + Kr)], &b.tcn_w[(size_t)r * Kt], sizeof(float) * Kt);
-        if (Kr) memcpy(&cat[(size_t)r * (Kt + Kr) + Kt], &b.res_w[(size_t)r * Kr], sizeof(float) * Kr);
+        if (bc.res_kind == COSK_RES_CONV) memcpy(&cat[(size_t)r * (Kt + Kr) + Kt], &b.res_w[(size_t)r * Kr], sizeof(float) * Kr);
+        else if (ident_k)
+          for (int k = 0; k < Kr; ++k) cat[(size_t)r * (Kt + Kr) + Kt + k] = k == r ? 1.0f : 0.0f;
       }
       std::vector<uint16_t> s = split_rows(cat, bc.cout, Kt + Kr);
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_tcn_w16), s.data(), s.size()))) return rc;
@@ -329,7 +349,9 @@ int zero_state(cosk_model *m, cudaStream_t s) {
   for (auto &b : m->blk) {
     CK(cudaMemsetAsync(b.ring.ptr, 0, b.ring.bytes(), s));
     CK(cudaMemsetAsync(b.out.ptr, 0, b.out.bytes(), s));
+    CK(cudaMemsetAsync(b.d_tile_cnt, 0, sizeof(unsigned int) * (size_t)(m->n_tiles + 2), s));
     b.n_in = b.n_out = 0;
+    b.merge_ticket = 0;
   }
   if (m->cfg.classes > 0) {
     const size_t cl = (size_t)m->cfg.blocks[m->cfg.n_blocks - 1].cout;
@@ -411,6 +433,121 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_tcn_gcn<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          std::max(TcTcnCfg<64>::kSmemBytes, TcGcnCfg<4, 1>::kSmemBytes)));
+  CK(cudaFuncSetAttribute(k_tc_tcn2_gcn<128, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          std::max(TcTcn2Cfg<128>::kSmemBytes, TcGcnCfg<4, 2>::kSmemBytes)));
+  return COSK_OK;
+}
+
+TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  TcGcnArgs a;
+  a.tm_x = in.map;
+  a.tm_w = b.map_gcn_w;
+  a.x_row = (int)in.row_hi(in_slot);
+  a.t_alloc = (int)m->t_alloc;
+  a.cin = bc.cin;
+  a.cout = bc.cout;
+  a.V = m->cfg.vertices;
+  a.n_tiles = m->n_tiles;
+  a.tile_tokens = m->tile_tokens;
+  a.n_tokens = m->n_tokens;
+  a.mix_ptr = b.d_mix_ptr;
+  a.mix_src = b.d_mix_src;
+  a.mix_val = b.d_mix_val;
+  a.trace = m->d_trace;
+  a.wait_cnt = nullptr;
+  a.wait_need = 0;
+  a.epi.bias = b.d_gcn_b;
+  a.epi.r_hi = b.gcn_parts == 4 ? nullptr : in.hi(in_slot);  // P = 3: identity gcn_residual added by the drain warps
+  a.epi.r_lo = b.gcn_parts == 4 ? nullptr : in.lo(in_slot);
+  a.epi.cs_r = in.cs;
+  a.epi.y_hi = b.ring.hi(ring_slot);
+  a.epi.y_lo = b.ring.lo(ring_slot);
+  a.epi.cs_out = b.ring.cs;
+  a.dbg = m->d_dbg;
+  return a;
+}
+
+TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, int out_slot) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  TcTcnArgs a;
+  a.tm_ring = b.ring.map;
+  a.tm_res = b.tcn_res_kblock ? in.map : b.ring.map;
+  a.tm_w = b.map_tcn_w;
+  for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
+  a.res_row = (int)in.row_hi(res_slot);
+  a.t_alloc = (int)m->t_alloc;
+  a.kb_per_tap = bc.cout / kBK;
+  a.kb_res = b.tcn_res_kblock ? bc.cin / kBK : 0;
+  a.n_tiles = m->n_tiles;
+  a.tile_tokens = m->tile_tokens;
+  a.reverse = m->tcn_reverse;
+  a.n_tokens = m->n_tokens;
+  a.epi.bias = b.d_tcn_b;
+  const bool epi_res = bc.res_kind == COSK_RES_IDENTITY && !b.tcn_res_kblock;
+  a.epi.r_hi = epi_res ? in.hi(res_slot) : nullptr;
+  a.epi.r_lo = epi_res ? in.lo(res_slot) : nullptr;
+  a.epi.cs_r = in.cs;
+  a.epi.y_hi = b.out.hi(out_slot);
+  a.epi.y_lo = b.out.lo(out_slot);
+  a.epi.cs_out = b.out.cs;
+  a.tile_cnt = nullptr;
+  a.trace = m->d_trace;
+  a.dbg = m->d_dbg;
+  return a;
+}
+
+// The temporal conv of block i and the graph conv of block i+1 in one cooperative launch (k_tc_tcn_gcn):
+// possible when both run on the tensor-core kernels, the temporal conv is one of the HBM-bound widths and
+// there are enough tiles to feed both CTA groups.
+bool can_merge(const cosk_model *m, int i) {
+  if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace) return false;
+  const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
+  const int c = m->cfg.blocks[i].cout;
+  if (!b.tc_tcn || !nb.tc_gcn || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
+  if (m->n_tiles < m->merge_min_tiles) return false;
+  if (c == 64) return m->gcn_single_stage && !(m->pair_mask & 1);
+  if (c == 128) return (m->pair_mask & 2) != 0;
+  return false;
+}
+
+int run_tcn_gcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, int out_slot, cudaStream_t s) {
+  BlockW &b = m->blk[i], &nb = m->blk[i + 1];
+  const int c = m->cfg.blocks[i].cout;
+  int rc = prof_mark(m, 2, i, s);
+  if (rc) return rc;
+  TcTcnArgs ta = make_tcn_args(m, i, in, res_slot, n, out_slot);
+  // the graph conv of block i+1 reads the output slot written here and pushes into its own ring
+  const long long n_next = nb.n_in;
+  TcGcnArgs ga = make_gcn_args(m, i + 1, b.out, out_slot, (int)(n_next % kRingSlots));
+  ta.reverse = 0;  // tiles are produced first to last, the order in which the other role consumes them
+  ta.tile_cnt = b.d_tile_cnt;
+  ga.wait_cnt = b.d_tile_cnt;
+  ga.wait_need = 4u * (unsigned)(++b.merge_ticket);  // four epilogue warps announce every tile of every launch
+  const int grid = m->num_sms & ~1;
+  int n_tcn = c == 64 ? m->merge_split64 : m->merge_split128;
+  n_tcn = (n_tcn < 2 ? 2 : (n_tcn > grid - 2 ? grid - 2 : n_tcn)) & ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(512);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // every CTA resident: the waiting role cannot starve the producer
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (c == 64) {
+    cfg.dynamicSmemBytes = std::max(TcTcnCfg<64>::kSmemBytes, TcGcnCfg<4, 1>::kSmemBytes);
+    CK(cudaLaunchKernelEx(&cfg, k_tc_tcn_gcn<64, 4, 1>, ta, ga, n_tcn));
+  } else {
+    cfg.dynamicSmemBytes = std::max(TcTcn2Cfg<128>::kSmemBytes, TcGcnCfg<4, 2>::kSmemBytes);
+    CK(cudaLaunchKernelEx(&cfg, k_tc_tcn2_gcn<128, 4, 2>, ta, ga, n_tcn));
+  }
+  m->launches++;
   return COSK_OK;
 }
 
@@ -421,29 +558,7 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
   int rc = prof_mark(m, 1, i, s);
   if (rc) return rc;
   if (b.tc_gcn) {
-    TcGcnArgs a;
-    a.tm_x = in.map;
-    a.tm_w = b.map_gcn_w;
-    a.x_row = (int)in.row_hi(in_slot);
-    a.t_alloc = (int)m->t_alloc;
-    a.cin = bc.cin;
-    a.cout = bc.cout;
-    a.V = m->cfg.vertices;
-    a.n_tiles = m->n_tiles;
-    a.tile_tokens = m->tile_tokens;
-    a.n_tokens = m->n_tokens;
-    a.mix_ptr = b.d_mix_ptr;
-    a.mix_src = b.d_mix_src;
-    a.mix_val = b.d_mix_val;
-    a.trace = m->d_trace;
-    a.epi.bias = b.d_gcn_b;
-    a.epi.r_hi = b.gcn_parts == 4 ? nullptr : in.hi(in_slot);  // P = 3: identity gcn_residual added by the drain warps
-    a.epi.r_lo = b.gcn_parts == 4 ? nullptr : in.lo(in_slot);
-    a.epi.cs_r = in.cs;
-    a.epi.y_hi = b.ring.hi(ring_slot);
-    a.epi.y_lo = b.ring.lo(ring_slot);
-    a.epi.cs_out = b.ring.cs;
-    a.dbg = m->d_dbg;
+    TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
     // one K-block per work item (cin = 64): single operand stage, four exchange buffers
     const bool one_kb = bc.cin == kBK && m->gcn_single_stage;
     if (b.gcn_parts == 4) rc = one_kb ? launch_tc_gcn<4, 1>(m, a, s) : launch_tc_gcn<4, 2>(m, a, s);
@@ -489,30 +604,12 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
   int tap_slot[kTaps];
   for (int k = 0; k < kTaps; ++k) tap_slot[k] = (int)((n + 1 + k) % kRingSlots);  // frame n-8+k
   if (b.tc_tcn) {
-    TcTcnArgs a;
-    a.tm_ring = b.ring.map;
-    a.tm_res = bc.res_kind == COSK_RES_CONV ? in.map : b.ring.map;
-    a.tm_w = b.map_tcn_w;
-    for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi(tap_slot[k]);
-    a.res_row = (int)in.row_hi(res_slot);
-    a.t_alloc = (int)m->t_alloc;
-    a.kb_per_tap = bc.cout / kBK;
-    a.kb_res = bc.res_kind == COSK_RES_CONV ? bc.cin / kBK : 0;
-    a.n_tiles = m->n_tiles;
-    a.tile_tokens = m->tile_tokens;
-    a.reverse = m->tcn_reverse;
-    a.n_tokens = m->n_tokens;
-    a.epi.bias = b.d_tcn_b;
-    a.epi.r_hi = bc.res_kind == COSK_RES_IDENTITY ? in.hi(res_slot) : nullptr;
-    a.epi.r_lo = bc.res_kind == COSK_RES_IDENTITY ? in.lo(res_slot) : nullptr;
-    a.epi.cs_r = in.cs;
-    a.epi.y_hi = b.out.hi(out_slot);
-    a.epi.y_lo = b.out.lo(out_slot);
-    a.epi.cs_out = b.out.cs;
-    a.dbg = m->d_dbg;
+    TcTcnArgs a = make_tcn_args(m, i, in, res_slot, n, out_slot);
     const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
     if (pair) {
-      a.tm_w = b.map_tcn_w_half;  // each CTA of a pair loads its own half of the weight rows
+      // stacked-B widths (<= 128): CTA 0 loads the whole hi plane, CTA 1 the whole lo plane (full-height box);
+      // C = 256: each CTA loads its half of the rows of both planes
+      if (bc.cout > 128) a.tm_w = b.map_tcn_w_half;
       if (bc.cout == 64) rc = launch_tc_tcn2<64>(m, a, s);
       else if (bc.cout == 128) rc = launch_tc_tcn2<128>(m, a, s);
       else rc = launch_tc_tcn2<256>(m, a, s);
@@ -577,6 +674,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   }
   const ActBuf *in = &m->xin;
   bool alive = true;
+  bool gcn_done = false;  // the graph conv of the current block already ran inside the previous block's merged launch
   for (int i = 0; i < c.n_blocks; ++i) {
     m->last_flags[i] = 0;
     if (!alive) continue;
@@ -584,11 +682,18 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const cosk_block_cfg &bc = c.blocks[i];
     const long long n = b.n_in;  // index of this input == index of the predecessor's emission
     const int in_slot = (int)(n % kOutSlots);
-    if ((rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) return rc;
+    if (!gcn_done && (rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) return rc;
+    gcn_done = false;
     const bool fire = tcn_fires(n, c.padding, bc.stride);
     if (fire) {
       const int res_slot = (int)((n - kResDelay) % kOutSlots);  // n >= first >= 4
-      if ((rc = run_tcn(m, i, *in, res_slot, n, (int)(b.n_out % kOutSlots), s))) return rc;
+      const int out_slot = (int)(b.n_out % kOutSlots);
+      if (can_merge(m, i)) {
+        if ((rc = run_tcn_gcn(m, i, *in, res_slot, n, out_slot, s))) return rc;
+        gcn_done = true;
+      } else if ((rc = run_tcn(m, i, *in, res_slot, n, out_slot, s))) {
+        return rc;
+      }
       b.n_out++;
     }
     b.n_in++;
@@ -680,6 +785,11 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_TCN_IDENTITY_MMA")) m->tcn_identity_mma = atoi(e);
+  if (const char *e = getenv("COSK_MERGE")) m->merge = atoi(e);
+  if (const char *e = getenv("COSK_MERGE_MIN_TILES")) m->merge_min_tiles = atoi(e);
+  if (const char *e = getenv("COSK_MERGE_SPLIT64")) m->merge_split64 = atoi(e);
+  if (const char *e = getenv("COSK_MERGE_SPLIT128")) m->merge_split128 = atoi(e);
   if (const char *e = getenv("COSK_GCN_SINGLE_STAGE")) m->gcn_single_stage = atoi(e);
   if (const char *e = getenv("COSK_TCN_REVERSE")) m->tcn_reverse = atoi(e);
   if (const char *e = getenv("COSK_GCN_IDENTITY_MMA")) m->gcn_identity_mma = atoi(e);
@@ -794,6 +904,7 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
   for (int i = 0; i < c.n_blocks; ++i) {
     if ((rc = alloc_act(m, m->blk[i].ring, kRingSlots, c.blocks[i].cout))) return rc;
     if ((rc = alloc_act(m, m->blk[i].out, kOutSlots, c.blocks[i].cout))) return rc;
+    CK(cudaMalloc(&m->blk[i].d_tile_cnt, sizeof(unsigned int) * (size_t)(m->n_tiles + 2)));
   }
   if (c.classes > 0) {
     const size_t cl = (size_t)c.blocks[c.n_blocks - 1].cout;

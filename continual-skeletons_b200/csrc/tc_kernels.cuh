@@ -32,6 +32,7 @@ enum : unsigned int {
   kDbgEpiTmemFull = 0x04000000u,
   kDbgEpiExchEmpty = 0x05000000u,
   kDbgEpiExchFull = 0x06000000u,
+  kDbgTileFlag = 0x07000000u,
 };
 
 struct PipeState {
@@ -51,16 +52,29 @@ template <int COUT>
 __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                              bool first) {
   constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, COUT);
-  const uint32_t a_sel[3] = {a_hi, a_lo, a_hi};
-  const uint32_t b_sel[3] = {b_hi, b_hi, b_lo};
+  const uint32_t ah = ptx::umma_desc_lo(a_hi), al = ptx::umma_desc_lo(a_lo), bh = ptx::umma_desc_lo(b_hi), bl = ptx::umma_desc_lo(b_lo);
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
+  for (int k = 0; k < kBK / 16; ++k) {  // one UMMA K-step = 32 bytes = 2 descriptor units
+    ptx::umma_bf16_lo(tmem_d, ah + 2 * k, bh + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    ptx::umma_bf16_lo(tmem_d, al + 2 * k, bh + 2 * k, idesc, 1u);
+    ptx::umma_bf16_lo(tmem_d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+  }
+}
+
+// "Stacked-B" form of the split-precision product for COUT <= 128: the weight tile's hi and lo planes sit
+// back to back in shared memory and are used as ONE operand of N' = 2*COUT rows, so a K-step is two MMAs
+// (A_hi and A_lo against [B_hi; B_lo]) instead of three.  Accumulator columns [0, COUT) collect
+// hi*hi + lo*hi, columns [COUT, 2*COUT) collect hi*lo + lo*lo; the epilogue adds the two halves.  A
+// tcgen05.mma costs a fixed ~85 cycles (the 128-row A fetch) plus ~0.2 cycles per accumulator column, so
+// fewer, wider instructions are what makes the narrow layers faster (and the lo*lo term comes for free).
+template <int N2>
+__device__ __forceinline__ void issue_kblock_stacked(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_stack, bool first) {
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, N2);
+  const uint32_t ah = ptx::umma_desc_lo(a_hi), al = ptx::umma_desc_lo(a_lo), bs = ptx::umma_desc_lo(b_stack);
 #pragma unroll
-    for (int k = 0; k < kBK / 16; ++k) {
-      const uint64_t da = ptx::umma_desc_sw128(a_sel[p] + k * 32);
-      const uint64_t db = ptx::umma_desc_sw128(b_sel[p] + k * 32);
-      ptx::umma_bf16(tmem_d, da, db, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
-    }
+  for (int k = 0; k < kBK / 16; ++k) {
+    ptx::umma_bf16_lo(tmem_d, ah + 2 * k, bs + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    ptx::umma_bf16_lo(tmem_d, al + 2 * k, bs + 2 * k, idesc, 1u);
   }
 }
 
@@ -74,7 +88,7 @@ struct EpiArgs {
 
 // One epilogue warp: 32 accumulator rows, COUT fp32 columns each -> bias, residual, ReLU, split,
 // 128-bit stores of the row's channel vector.
-template <int COUT>
+template <int COUT, bool STACKED>
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr_row0, const float *bias_s, const EpiArgs &e, long long tok,
                                               bool valid) {
 #pragma unroll 1
@@ -82,10 +96,18 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr_row0, const float *
     uint32_t r[32];
     ptx::tmem_ld_32x32(taddr_row0 + c0, r);
     ptx::tmem_ld_wait();
-    if (valid) {
-      float v[32];
+    float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + bias_s[c0 + j];
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (STACKED) {  // second half of the stacked accumulator: hi*lo + lo*lo
+      ptx::tmem_ld_32x32(taddr_row0 + COUT + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] += bias_s[c0 + j];
       if (e.r_hi != nullptr) {
         const uint4 *ph = reinterpret_cast<const uint4 *>(e.r_hi + tok * e.cs_r + c0);
         const uint4 *pl = reinterpret_cast<const uint4 *>(e.r_lo + tok * e.cs_r + c0);
@@ -137,6 +159,10 @@ struct TcTcnArgs {
                 // so the most recently written rows -- the ones still in L2 -- are consumed first
   long long n_tokens;
   EpiArgs epi;
+  unsigned long long *trace;  // optional phase timers of CTA 0 (COSK_TRACE=1): [24] producer wait, [25] producer total,
+                              // [26] MMA wait operands, [27] MMA wait accumulator, [28] MMA total
+  unsigned int *tile_cnt;  // optional [n_tiles] counters: each epilogue warp adds 1 once its rows of a tile are stored
+                           // (release), so a graph-conv role of the same launch can start on that tile
   unsigned int *dbg;
 };
 
@@ -145,22 +171,26 @@ struct TcTcnCfg {
   // Activations (HBM latency) and weights (L2 latency) travel in separate rings so that the
   // activation ring can be one stage deeper where shared memory is tight (COUT = 256).
   static constexpr int kBBytes = COUT * kBK * 2;
-  static constexpr int kAStages = COUT == 64 ? 4 : 3;
-  static constexpr int kBStages = COUT == 64 ? 4 : (COUT == 128 ? 3 : 2);
+  static constexpr int kAStages = COUT == 64 ? 5 : 3;
+  static constexpr int kBStages = COUT == 64 ? 3 : (COUT == 128 ? 3 : 2);
   static constexpr int kAOff = 0;
   static constexpr int kBOff = kAStages * 2 * kABytes;
   static constexpr int kBarOff = kBOff + kBStages * 2 * kBBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + COUT * 4 + 1024;  // + slack for manual 1024-B alignment
-  static constexpr int kTmemCols = 2 * COUT;                     // double-buffered accumulator
+  static constexpr bool kStacked = COUT <= 128;                  // two MMAs per K-step against [B_hi; B_lo]
+  static constexpr int kAccCols = kStacked ? 2 * COUT : COUT;
+  static constexpr int kTmemCols = 2 * kAccCols;                 // double-buffered accumulator
   static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
 };
 
+// Role bodies are device functions so that one launch can run the temporal conv of block L on some CTAs
+// and the graph conv of block L+1 on the others (k_tc_tcn_gcn below).  `cta` / `ncta` = index of this CTA
+// among the CTAs running the role and their count.
 template <int COUT>
-__global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcnArgs a) {
+__device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, const int cta, const int ncta) {
   using Cfg = TcTcnCfg<COUT>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window: align on the shared address
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *afull = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
@@ -209,12 +239,17 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
     if (lane == 0) {
       PipeState pa, pb;
       bool ok = true;
-      for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x) {
-        const int tile = a.reverse ? (int)blockIdx.x + (int)gridDim.x * ((a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x) - (ti - (int)blockIdx.x) : ti;
+      const bool tr = a.trace != nullptr && cta == 0;
+      unsigned long long tw = 0;
+      const long long tstart = tr ? clock64() : 0;
+      for (int ti = cta; ok && ti < a.n_tiles; ti += ncta) {
+        const int tile = a.reverse ? cta + ncta * ((a.n_tiles - 1 - cta) / ncta) - (ti - cta) : ti;
         const int tok0 = tile * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
+          const long long w0 = tr ? clock64() : 0;
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
           if (!ok) break;
+          if (tr) tw += clock64() - w0;
           const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
           ptx::mbar_arrive_expect_tx(&afull[pa.stage], 2 * kABytes);
           const CUtensorMap *tm;
@@ -243,27 +278,39 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
           pb.advance<Cfg::kBStages>();
         }
       }
+      if (tr) {
+        a.trace[24] = tw;
+        a.trace[25] = clock64() - tstart;
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       PipeState pa, pb;
       bool ok = true;
       int it = 0;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const bool tr = a.trace != nullptr && cta == 0;
+      unsigned long long tw_ops = 0, tw_acc = 0;
+      const long long tstart = tr ? clock64() : 0;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta, ++it) {
         const int acc = it & 1;
+        const long long w0 = tr ? clock64() : 0;
         ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
         if (!ok) break;
+        if (tr) tw_acc += clock64() - w0;
         ptx::tc_fence_after();
-        const uint32_t d = tmem_base + acc * COUT;
+        const uint32_t d = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < nkb; ++kb) {
+          const long long w1 = tr ? clock64() : 0;
           ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaFull | (unsigned)kb);
           if (!ok) break;
           ok = ptx::mbar_wait(&bfull[pb.stage], pb.phase, a.dbg, kDbgMmaFull | 0x800000u | (unsigned)kb);
           if (!ok) break;
+          if (tr) tw_ops += clock64() - w1;
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
           const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBBytes;
-          issue_kblock<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBBytes, kb == 0);
+          if (Cfg::kStacked) issue_kblock_stacked<2 * COUT>(d, sa, sa + kABytes, sb, kb == 0);
+          else issue_kblock<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBBytes, kb == 0);
           ptx::umma_commit(&aempty[pa.stage]);
           ptx::umma_commit(&bempty[pb.stage]);
           pa.advance<Cfg::kAStages>();
@@ -271,13 +318,18 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
         }
         if (ok) ptx::umma_commit(&tfull[acc]);
       }
+      if (tr) {
+        a.trace[26] = tw_ops;
+        a.trace[27] = tw_acc;
+        a.trace[28] = clock64() - tstart;
+      }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
-    for (int ti = blockIdx.x; ok && ti < a.n_tiles; ti += gridDim.x, ++it) {
-      const int tile = a.reverse ? (int)blockIdx.x + (int)gridDim.x * ((a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x) - (ti - (int)blockIdx.x) : ti;
+    for (int ti = cta; ok && ti < a.n_tiles; ti += ncta, ++it) {
+      const int tile = a.reverse ? cta + ncta * ((a.n_tiles - 1 - cta) / ncta) - (ti - cta) : ti;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
@@ -285,15 +337,25 @@ __global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcn
       const int row = q * 32 + lane;
       const long long tok = (long long)tile * a.tile_tokens + row;
       const bool valid = row < a.tile_tokens && tok < a.n_tokens;
-      epilogue_rows<COUT>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * COUT, bias_s, a.epi, tok, valid);
+      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, a.epi, tok, valid);
       ptx::tc_fence_before();
+      if (a.tile_cnt != nullptr) __threadfence();  // this lane's output rows are visible device-wide ...
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        ptx::mbar_arrive(&tempty[acc]);
+        if (a.tile_cnt != nullptr) atomicAdd(a.tile_cnt + tile, 1u);  // ... before the tile is announced
+      }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(256, 1) k_tc_tcn(const __grid_constant__ TcTcnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tcn_body<COUT>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // =============================================================================================
@@ -314,31 +376,41 @@ struct TcTcn2Cfg {
   static constexpr int kBarOff = kBOff + kBStages * 2 * kBHalfBytes;
   static constexpr int kBiasOff = kBarOff + 256;
   static constexpr int kSmemBytes = kBiasOff + COUT * 4 + 1024;
-  static constexpr int kTmemCols = 2 * COUT;
+  // stacked-B (see issue_kblock_stacked): CTA 0 of the pair holds the whole B_hi plane, CTA 1 the whole B_lo plane,
+  // i.e. the two halves of the N' = 2*COUT operand rows that cta_group::2 splits across the pair
+  static constexpr bool kStacked = COUT <= 128;
+  static constexpr int kAccCols = kStacked ? 2 * COUT : COUT;
+  static constexpr int kTmemCols = 2 * kAccCols;
   static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
 };
+
+template <int N2>
+__device__ __forceinline__ void issue_kblock_pair_stacked(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_stack, bool first) {
+  constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileRows, N2);
+  const uint32_t ah = ptx::umma_desc_lo(a_hi), al = ptx::umma_desc_lo(a_lo), bs = ptx::umma_desc_lo(b_stack);
+#pragma unroll
+  for (int k = 0; k < kBK / 16; ++k) {
+    ptx::umma_bf16_pair_lo(tmem_d, ah + 2 * k, bs + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    ptx::umma_bf16_pair_lo(tmem_d, al + 2 * k, bs + 2 * k, idesc, 1u);
+  }
+}
 
 template <int COUT>
 __device__ __forceinline__ void issue_kblock_pair(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                                   bool first) {
   constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * kTileRows, COUT);
-  const uint32_t a_sel[3] = {a_hi, a_lo, a_hi};
-  const uint32_t b_sel[3] = {b_hi, b_hi, b_lo};
+  const uint32_t ah = ptx::umma_desc_lo(a_hi), al = ptx::umma_desc_lo(a_lo), bh = ptx::umma_desc_lo(b_hi), bl = ptx::umma_desc_lo(b_lo);
 #pragma unroll
-  for (int p = 0; p < 3; ++p) {
-#pragma unroll
-    for (int k = 0; k < kBK / 16; ++k) {
-      const uint64_t da = ptx::umma_desc_sw128(a_sel[p] + k * 32);
-      const uint64_t db = ptx::umma_desc_sw128(b_sel[p] + k * 32);
-      ptx::umma_bf16_pair(tmem_d, da, db, idesc, (first && p == 0 && k == 0) ? 0u : 1u);
-    }
+  for (int k = 0; k < kBK / 16; ++k) {
+    ptx::umma_bf16_pair_lo(tmem_d, ah + 2 * k, bh + 2 * k, idesc, (first && k == 0) ? 0u : 1u);
+    ptx::umma_bf16_pair_lo(tmem_d, al + 2 * k, bh + 2 * k, idesc, 1u);
+    ptx::umma_bf16_pair_lo(tmem_d, ah + 2 * k, bl + 2 * k, idesc, 1u);
   }
 }
 
 template <int COUT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(const __grid_constant__ TcTcnArgs a) {
+__device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw, const int cluster_id, const int n_clusters) {
   using Cfg = TcTcn2Cfg<COUT>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *afull = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
   uint64_t *aempty = afull + Cfg::kAStages;
@@ -384,8 +456,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
   pdl_wait();
   const int nkb = kTaps * a.kb_per_tap + a.kb_res;
   const int n_pairs = (a.n_tiles + 1) / 2;
-  const int n_clusters = gridDim.x / 2;
-  const int cluster_id = blockIdx.x / 2;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -420,8 +490,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
           const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBHalfBytes;
           if (leader) ptx::mbar_arrive_expect_tx(&bfull[pb.stage], 2 * 2 * Cfg::kBHalfBytes);
           const uint32_t fb = ptx::mapa_u32(ptx::smem_u32(&bfull[pb.stage]), 0);
-          ptx::tma_load_2d_pair_hint(sb, &a.tm_w, fb, kb * kBK, (int)rank * (COUT / 2), ptx::kEvictLast);
-          ptx::tma_load_2d_pair_hint(sb + Cfg::kBHalfBytes, &a.tm_w, fb, kb * kBK, COUT + (int)rank * (COUT / 2), ptx::kEvictLast);
+          if (Cfg::kStacked) {
+            // one box of COUT rows: the hi plane for CTA 0, the lo plane for CTA 1 (tm_w then has a COUT-row box)
+            ptx::tma_load_2d_pair_hint(sb, &a.tm_w, fb, kb * kBK, (int)rank * COUT, ptx::kEvictLast);
+          } else {
+            ptx::tma_load_2d_pair_hint(sb, &a.tm_w, fb, kb * kBK, (int)rank * (COUT / 2), ptx::kEvictLast);
+            ptx::tma_load_2d_pair_hint(sb + Cfg::kBHalfBytes, &a.tm_w, fb, kb * kBK, COUT + (int)rank * (COUT / 2), ptx::kEvictLast);
+          }
           pb.advance<Cfg::kBStages>();
         }
       }
@@ -436,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
         ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
         if (!ok) break;
         ptx::tc_fence_after();
-        const uint32_t d = tmem_base + acc * COUT;
+        const uint32_t d = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaFull | (unsigned)kb);
           if (!ok) break;
@@ -445,7 +520,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + Cfg::kAOff + pa.stage * 2 * kABytes;
           const uint32_t sb = smem_base + Cfg::kBOff + pb.stage * 2 * Cfg::kBHalfBytes;
-          issue_kblock_pair<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBHalfBytes, kb == 0);
+          if (Cfg::kStacked) issue_kblock_pair_stacked<2 * COUT>(d, sa, sa + kABytes, sb, kb == 0);
+          else issue_kblock_pair<COUT>(d, sa, sa + kABytes, sb, sb + Cfg::kBHalfBytes, kb == 0);
           ptx::umma_commit_pair(&aempty[pa.stage], 3);
           ptx::umma_commit_pair(&bempty[pb.stage], 3);
           pa.advance<Cfg::kAStages>();
@@ -454,7 +530,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
         if (ok) ptx::umma_commit_pair(&tfull[acc], 3);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
@@ -468,15 +544,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(co
       const int row = q * 32 + lane;
       const long long tok = (long long)tile * a.tile_tokens + row;
       const bool valid = tile < a.n_tiles && row < a.tile_tokens && tok < a.n_tokens;
-      epilogue_rows<COUT>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * COUT, bias_s, a.epi, tok, valid);
+      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, a.epi, tok, valid);
       ptx::tc_fence_before();
+      if (a.tile_cnt != nullptr) __threadfence();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
+      if (lane == 0) {
+        ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
+        if (a.tile_cnt != nullptr && tile < a.n_tiles) atomicAdd(a.tile_cnt + tile, 1u);
+      }
     }
   }
   ptx::tc_fence_before();
   ptx::cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal or read
   if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+}
+
+template <int COUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) k_tc_tcn2(const __grid_constant__ TcTcnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  tcn2_body<COUT>(a, smem_raw, (int)blockIdx.x / 2, (int)gridDim.x / 2);
 }
 
 // =============================================================================================
@@ -512,6 +598,8 @@ struct TcGcnArgs {
   const int *mix_src;
   const float *mix_val;
   unsigned long long *trace;  // optional phase timers written by CTA 0 (COSK_TRACE=1), else nullptr
+  const unsigned int *wait_cnt;  // optional [n_tiles] counters of the temporal conv that produces the input rows in
+  unsigned int wait_need;        // the same launch: tile t may be loaded once wait_cnt[t] >= wait_need
   EpiArgs epi;                // r_hi/r_lo = input rows when cin == cout (identity gcn_residual, P = 3), else nullptr
   unsigned int *dbg;
 };
@@ -575,9 +663,8 @@ __device__ __forceinline__ void mix_gather(const uint8_t *buf, const uint32_t (&
 }
 
 template <int P, int STAGES, bool TRACE>
-__global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
+__device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, const int cta, const int ncta) {
   using Cfg = TcGcnCfg<P, STAGES>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
   uint64_t *empty = full + Cfg::kStages;
@@ -661,8 +748,22 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
     if (lane == 0) {
       PipeState ps;
       bool ok = true;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
         const int row = a.x_row + tile * a.tile_tokens;
+        if (a.wait_cnt != nullptr) {
+          // the input rows of this tile come from the temporal-conv role of the same launch
+          const long long t0 = clock64();
+          while (ptx::ld_acquire_u32(a.wait_cnt + tile) < a.wait_need) {
+            if (*(volatile unsigned int *)a.dbg != 0 || clock64() - t0 > ptx::kWaitLimitCycles) {
+              atomicCAS(a.dbg, 0u, kDbgTileFlag | (unsigned)(tile & 0xffffff));
+              ok = false;
+              break;
+            }
+            __nanosleep(200);
+          }
+          if (!ok) break;
+          ptx::fence_proxy_async_all();  // order the acquire (generic proxy) before the TMA reads (async proxy)
+        }
         for (int pass = 0; ok && pass < n_pass; ++pass) {
           for (int kc = 0; kc < nkb; ++kc) {
             ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(pass * 16 + kc));
@@ -686,10 +787,10 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
       PipeState ps;
       bool ok = true;
       int it = 0;
-      const bool mtr = TRACE && a.trace != nullptr && blockIdx.x == 0;
+      const bool mtr = TRACE && a.trace != nullptr && cta == 0;
       unsigned long long mt[2] = {0, 0};
       const long long mstart = mtr ? clock64() : 0;
-      for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
         for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
           const int acc = it & 1;
           const long long m0 = mtr ? clock64() : 0;
@@ -728,7 +829,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
       const int e0 = a.mix_ptr[wv];
       if (a.mix_ptr[wv + 1] > e0) d0 = a.mix_val[e0];
     }
-    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && q == 0 && lane == 0;
+    const bool tr = TRACE && a.trace != nullptr && cta == 0 && q == 0 && lane == 0;
     unsigned long long tr_t[4] = {0, 0, 0, 0};
     long long tr_c = 0;
     const long long tr_start = tr ? clock64() : 0;
@@ -750,8 +851,8 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
         xr[0] = xr[1] = xr[2] = xr[3] = make_uint4(0, 0, 0, 0);
       }
     };
-    if (blockIdx.x < a.n_tiles) fetch_res(blockIdx.x, 0);
-    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+    if (cta < a.n_tiles) fetch_res(cta, 0);
+    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
       for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
         const int acc = it & 1;
         if (tr) tr_c = clock64();
@@ -777,7 +878,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
             int nt = tile, nc0 = c0 + kGcnChunk;
             if (nc0 >= a.cout) {
               nc0 = 0;
-              nt = tile + gridDim.x;
+              nt = tile + ncta;
             }
             if (nt < a.n_tiles) fetch_res(nt, nc0);
           }
@@ -855,12 +956,12 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-    const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && m == 0 && lane == 0;
+    const bool tr = TRACE && a.trace != nullptr && cta == 0 && m == 0 && lane == 0;
     unsigned long long tr_t[3] = {0, 0, 0};
     long long tr_c = 0;
     bool ok = true;
     uint32_t xc = 0;
-    for (int tile = blockIdx.x; ok && tile < a.n_tiles; tile += gridDim.x) {
+    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
       const long long tok0 = (long long)tile * a.tile_tokens;
       for (int pass = 0; ok && pass < n_pass; ++pass) {
 #pragma unroll 1
@@ -909,6 +1010,37 @@ __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcn
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int P, int STAGES, bool TRACE>
+__global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  gcn_body<P, STAGES, TRACE>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// =============================================================================================
+// One launch, two roles: CTAs [0, n_tcn) run the temporal conv of block L, the remaining CTAs the graph
+// conv of block L+1, which consumes the temporal conv's output tile by tile (per-tile release/acquire
+// counters in global memory).  The temporal convs of the 64- and 128-channel layers are bound by HBM and
+// leave the SMs' issue slots, tensor pipe and TMEM idle, while the graph conv is bound by its epilogue and
+// barely touches HBM: side by side the pair finishes in about the time of the temporal conv alone.
+// Launched cooperatively (all CTAs co-resident), so the waiting role cannot starve the producing one.
+// =============================================================================================
+template <int COUT, int P, int STAGES>
+__global__ void __launch_bounds__(512, 1) k_tc_tcn_gcn(const __grid_constant__ TcTcnArgs ta, const __grid_constant__ TcGcnArgs ga,
+                                                       const int n_tcn) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((int)blockIdx.x < n_tcn) tcn_body<COUT>(ta, smem_raw, (int)blockIdx.x, n_tcn);
+  else gcn_body<P, STAGES, false>(ga, smem_raw, (int)blockIdx.x - n_tcn, (int)gridDim.x - n_tcn);
+}
+
+// same with the temporal conv on CTA pairs: the role is chosen per cluster
+template <int COUT, int P, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+    k_tc_tcn2_gcn(const __grid_constant__ TcTcnArgs ta, const __grid_constant__ TcGcnArgs ga, const int n_tcn) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((int)blockIdx.x < n_tcn) tcn2_body<COUT>(ta, smem_raw, (int)blockIdx.x / 2, n_tcn / 2);
+  else gcn_body<P, STAGES, false>(ga, smem_raw, (int)blockIdx.x - n_tcn, (int)gridDim.x - n_tcn);
 }
 
 }  // namespace cosk
