@@ -38,6 +38,31 @@ BLOCK_CASES = [
 ]
 BLOCK_T, BLOCK_B = 24, 2
 
+# the same block with AdaptiveGraphConvolution evaluated one frame at a time (CoAGcn's step semantics:
+# models/coa_gcn/coa_gcn.py:11-14 wraps the module in co.forward_stepping, i.e. T = 1 per call)
+ADAPTIVE_BLOCK_CASES = [
+    ("a_nores_p4", 4, 4, 1, False, 4),
+    ("a_idres_p4", 4, 4, 1, True, 4),
+    ("a_convres_s2_p4", 2, 4, 2, True, 4),
+    ("a_first_p4", 3, 64, 1, False, 4),
+    ("a_wide_idres_p4", 64, 64, 1, True, 4),
+    ("a_wide_convres_s2_p4", 64, 128, 2, True, 4),
+    ("a_wide_convres_p4", 128, 256, 1, True, 4),
+    ("a_wide_idres256_p4", 256, 256, 1, True, 4),
+]
+
+
+def per_frame_adaptive(ref):
+    """The reference's AdaptiveGraphConvolution applied frame by frame: what forward_step computes, laid
+    out as a clip so that the reference's SpatioTemporalBlock can run the temporal part."""
+
+    class PerFrameAdaptiveGraphConvolution(ref.AdaptiveGraphConvolution):
+        def forward(self, x):
+            fwd = super().forward
+            return torch.cat([fwd(x[:, :, t: t + 1]) for t in range(x.shape[2])], dim=2)
+
+    return PerFrameAdaptiveGraphConvolution
+
 
 class RefStack(nn.Module):
     """Reference SpatioTemporalBlocks wired like StGcn / StGcnMod (st_gcn.py:27-46)."""
@@ -47,9 +72,10 @@ class RefStack(nn.Module):
         if arch.head:
             self.data_bn = nn.BatchNorm1d(arch.persons * arch.c_in * arch.vertices)
         tp = -1 if arch.padding == 4 else arch.padding
+        kw = {"GraphConv": per_frame_adaptive(ref)} if arch.graph_conv == "adaptive" else {}
         self.layers = nn.ModuleDict(
             {
-                n.split(".")[-2]: ref.SpatioTemporalBlock(b.cin, b.cout, A, stride=b.stride, residual=b.residual, temporal_padding=tp)
+                n.split(".")[-2]: ref.SpatioTemporalBlock(b.cin, b.cout, A, stride=b.stride, residual=b.residual, temporal_padding=tp, **kw)
                 for n, b in zip(arch.block_names, arch.blocks)
             }
         )
@@ -93,6 +119,28 @@ def block_fixtures(ref):
     return out
 
 
+def adaptive_block_fixtures(ref):
+    out = {}
+    A = ref.ntu_A
+    gc = per_frame_adaptive(ref)
+    for idx, (name, cin, cout, stride, residual, pad) in enumerate(ADAPTIVE_BLOCK_CASES):
+        for rnd in (False, True):
+            arch = weights.ArchSpec([BlockSpec(cin, cout, stride, residual)], padding=pad, head=False, block_names=[""], graph_conv="adaptive")
+            sd = weights.make_state_dict(arch, seed=3000 + idx, randomize=rnd)
+            blk = ref.SpatioTemporalBlock(cin, cout, A, stride=stride, residual=residual, temporal_padding=pad, GraphConv=gc)
+            blk.load_state_dict(sd, strict=True)
+            blk.eval()
+            batch = 1 if "wide" in name else BLOCK_B
+            frames = 14 if "wide" in name else BLOCK_T  # keep the fixture small
+            x = weights.make_input((batch, cin, frames, 25), seed=4000 + idx)
+            with torch.no_grad():
+                y = blk(x)
+                g = blk.gcn(x[:, :, :2])  # graph conv alone on two frames
+            out[f"{name}{'_rnd' if rnd else ''}"] = y.numpy()
+            out[f"{name}{'_rnd' if rnd else ''}_gcn"] = g.numpy()
+    return out
+
+
 def model_fixtures(ref, arch_fn, tag, n=2):
     out = {}
     for rnd in (False, True):
@@ -124,10 +172,18 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, "adjacency.npz"), ntu=ref.ntu_A, kinetics=ref.kinetics_A)
-    np.savez_compressed(os.path.join(OUT, "blocks.npz"), **block_fixtures(ref))
-    np.savez_compressed(os.path.join(OUT, "cost_gcn.npz"), **model_fixtures(ref, weights.cost_gcn_arch, "cost_gcn"))
-    np.savez_compressed(os.path.join(OUT, "cost_gcn_mod.npz"), **model_fixtures(ref, weights.cost_gcn_mod_arch, "cost_gcn_mod"))
+    only = set(sys.argv[1:])  # e.g. ``python -m oracle.make_golden coa_gcn`` regenerates just that file
+
+    def save(name, make):
+        if not only or name in only:
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **make())
+
+    save("adjacency", lambda: dict(ntu=ref.ntu_A, kinetics=ref.kinetics_A))
+    save("blocks", lambda: block_fixtures(ref))
+    save("cost_gcn", lambda: model_fixtures(ref, weights.cost_gcn_arch, "cost_gcn"))
+    save("cost_gcn_mod", lambda: model_fixtures(ref, weights.cost_gcn_mod_arch, "cost_gcn_mod"))
+    save("coa_blocks", lambda: adaptive_block_fixtures(ref))
+    save("coa_gcn", lambda: model_fixtures(ref, weights.coa_gcn_arch, "coa_gcn"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -5,8 +5,8 @@ Test infrastructure only; usable ONLY in the build container (the GPU box has no
 ``continual`` at import time (datasets/datasets.py:4-7, models/base.py:6,10-11), none of which is
 installed, so their package ``__init__`` files are bypassed with namespace modules and three
 import-only stubs are registered (recipe: SURVEY.md Appendix A).  What comes out is the reference's
-real ``GraphConvolution`` / ``TemporalConvolution`` / ``SpatioTemporalBlock`` / ``init_weights`` /
-``graph.A``; the ``Co*`` factories are NOT usable (they need the real library).
+real ``GraphConvolution`` / ``AdaptiveGraphConvolution`` / ``TemporalConvolution`` /
+``SpatioTemporalBlock`` / ``init_weights`` / ``graph.A``; the ``Co*`` factories are NOT usable (they need the real library).
 """
 import importlib
 import os
@@ -47,7 +47,11 @@ def load():
     class _RideMixin:
         pass
 
-    _stub("ride", getLogger=logging.getLogger)
+    # class-statement-only stand-ins for what models/a_gcn/a_gcn.py:72-78 lists as bases of AGcn
+    ride = _stub("ride", getLogger=logging.getLogger, Configs=_Configs, RideModule=type("RideModule", (), {}),
+                 TopKAccuracyMetric=lambda *k: type("TopKAccuracyMetric", (), {}),
+                 SgdOneCycleOptimizer=type("SgdOneCycleOptimizer", (), {}))
+    ride.finetune = _stub("ride.finetune", Finetunable=type("Finetunable", (), {}))
     _stub("ride.core", Configs=_Configs, RideMixin=_RideMixin)
     _stub("ride.logging", getLogger=logging.getLogger)
     _stub("continual", Sequential=nn.Sequential)
@@ -57,6 +61,13 @@ def load():
         sys.modules[pkg] = ns
     for mod in ("datasets.graph", "datasets.ntu_rgbd", "datasets.kinetics", "models.utils", "models.base"):
         importlib.import_module(mod)
+    # datasets/datasets.py needs ride + pytorch_lightning; a_gcn.py only names datasets.GraphDatasets as a base
+    _stub("datasets.datasets", GraphDatasets=type("GraphDatasets", (), {}))
+    sys.modules["datasets"].datasets = sys.modules["datasets.datasets"]
+    ns = types.ModuleType("models.a_gcn")
+    ns.__path__ = [os.path.join(REF_ROOT, "models", "a_gcn")]
+    sys.modules["models.a_gcn"] = ns
+    importlib.import_module("models.a_gcn.a_gcn")
     sys.modules["models.base"]._cosk_shim = True
     return _namespace()
 
@@ -67,6 +78,7 @@ def _namespace():
         GraphConvolution=base.GraphConvolution,
         TemporalConvolution=base.TemporalConvolution,
         SpatioTemporalBlock=base.SpatioTemporalBlock,
+        AdaptiveGraphConvolution=sys.modules["models.a_gcn.a_gcn"].AdaptiveGraphConvolution,
         init_weights=utils.init_weights,
         ntu_A=sys.modules["datasets.ntu_rgbd"].graph.A,
         kinetics_A=sys.modules["datasets.kinetics"].graph.A,

@@ -25,8 +25,40 @@ def _conv(x, sd, key, stride=1, pad=0):
     return F.conv2d(x, sd[key + "weight"].to(x.dtype), sd[key + "bias"].to(x.dtype), stride=(stride, 1), padding=(pad, 0))
 
 
-def graph_conv(x, sd, key):
-    """x (B, Cin, T, V) -> (B, Cout, T, V).  models/base.py:260-270."""
+def adaptive_graph_conv(x, sd, key):
+    """AdaptiveGraphConvolution.forward, models/a_gcn/a_gcn.py:48-69: learned dense ``A + graph_attn`` plus a
+    per-sample vertex attention softmax(theta^T phi / (inter_c*T)) over the source vertex (dim -2).  The
+    attention spans all T frames of ``x``; the continual model (models/coa_gcn/coa_gcn.py:11-14,
+    ``co.forward_stepping``) calls it with T = 1."""
+    B, C, T, V = x.shape
+    adj = (sd[key + "A"] + sd[key + "graph_attn"]).to(x.dtype)
+    total = None
+    for part in range(3):
+        theta = _conv(x, sd, key + f"a_conv.{part}.")  # (B, inter_c, T, V)
+        phi = _conv(x, sd, key + f"b_conv.{part}.")
+        inter_c = theta.shape[1]
+        a1 = theta.permute(0, 3, 1, 2).reshape(B, V, inter_c * T)
+        a2 = phi.reshape(B, inter_c * T, V)
+        att = torch.softmax(torch.matmul(a1, a2) / (inter_c * T), dim=-2) + adj[part]
+        mixed = torch.matmul(x.reshape(B, C * T, V), att).reshape(B, C, T, V)
+        z = _conv(mixed, sd, key + f"g_conv.{part}.")
+        total = z + total if total is not None else z
+    total = _bn(total, sd, key + "bn.")
+    if (key + "gcn_residual.0.weight") in sd:
+        skip = _bn(_conv(x, sd, key + "gcn_residual.0."), sd, key + "gcn_residual.1.")
+    else:
+        skip = x
+    return F.relu(total + skip)
+
+
+def graph_conv(x, sd, key, per_frame=False):
+    """x (B, Cin, T, V) -> (B, Cout, T, V).  models/base.py:260-270; dispatches to the adaptive variant when
+    the state_dict holds its embedding convs.  ``per_frame`` evaluates the adaptive attention one frame at a
+    time, which is what the continual model does step by step."""
+    if (key + "a_conv.0.weight") in sd:
+        if per_frame and x.shape[2] > 1:
+            return torch.cat([adaptive_graph_conv(x[:, :, t: t + 1], sd, key) for t in range(x.shape[2])], dim=2)
+        return adaptive_graph_conv(x, sd, key)
     B, C, T, V = x.shape
     adj = (sd[key + "A"] * sd[key + "graph_attn"]).to(x.dtype)
     total = None
@@ -47,9 +79,9 @@ def temporal_conv(x, sd, key, stride, pad):
     return _bn(_conv(x, sd, key + "t_conv.", stride, pad), sd, key + "bn.")
 
 
-def st_block(x, sd, key, spec, pad):
+def st_block(x, sd, key, spec, pad, per_frame=False):
     """models/base.py:376-387; ``pad`` is temporal_padding (4 regular / 0 for the * variant)."""
-    z = temporal_conv(graph_conv(x, sd, key + "gcn."), sd, key + "tcn.", spec.stride, pad)
+    z = temporal_conv(graph_conv(x, sd, key + "gcn.", per_frame), sd, key + "tcn.", spec.stride, pad)
     shrink = 4 - pad
     xs = x[:, :, shrink: x.shape[2] - shrink] if shrink else x
     if spec.res_kind == 0:
@@ -69,10 +101,10 @@ def normalise_input(x, sd):
     return y.view(N, M, V, C, T).permute(0, 1, 3, 4, 2).contiguous().view(N * M, C, T, V)
 
 
-def stack_features(x, sd, arch, collect=None):
+def stack_features(x, sd, arch, collect=None, per_frame=False):
     """Run all blocks on a clip (N*M, C, T, V); optionally collect per-block outputs."""
     for name, spec in zip(arch.block_names, arch.blocks):
-        x = st_block(x, sd, name, spec, arch.padding)
+        x = st_block(x, sd, name, spec, arch.padding, per_frame)
         if collect is not None:
             collect.append(x)
     return x
@@ -87,19 +119,19 @@ def stgcn_forward(x, sd, arch, collect=None):
     return F.linear(y, sd["fc.weight"].to(y.dtype), sd["fc.bias"].to(y.dtype))
 
 
-def pooled_sequence(x, sd, arch):
+def pooled_sequence(x, sd, arch, per_frame=False):
     """(N, C, T, V, M) -> spatially pooled last-block features (N, Cl, T_out).  base.py:84."""
     N, M = x.shape[0], x.shape[4]
-    y = stack_features(normalise_input(x, sd), sd, arch)
+    y = stack_features(normalise_input(x, sd), sd, arch, per_frame=per_frame)
     _, c, t, v = y.shape
     return y.view(N, M, c, t, v).mean(4).mean(1)
 
 
-def co_clip_forward(x, sd, arch):
+def co_clip_forward(x, sd, arch, per_frame=False):
     """What CoStGcn/CoStGcnMod ``forward`` returns in clip mode: AvgPool1d(pool_size, 1,
     pool_padding) over the pooled sequence, fc per time step, first step kept
     (models/base.py:97-101,166-181)."""
-    h = pooled_sequence(x, sd, arch)
+    h = pooled_sequence(x, sd, arch, per_frame)
     h = F.avg_pool1d(h, arch.pool_size, stride=1, padding=arch.pool_padding)  # count_include_pad
     logits = torch.einsum("kc,nct->nkt", sd["fc.weight"].to(h.dtype), h) + sd["fc.bias"].to(h.dtype)[None, :, None]
     return logits[:, :, 0]

@@ -46,6 +46,7 @@ class ArchSpec:
     pool_size: int = -1
     pool_padding: int = -1
     block_names: List[str] = field(default_factory=list)
+    graph_conv: str = "plain"  # "plain": GraphConvolution (models/base.py:230-270); "adaptive": models/a_gcn/a_gcn.py:12-69
 
     def __post_init__(self):
         if not self.block_names:
@@ -85,6 +86,11 @@ def cost_gcn_mod_arch(skeleton="ntu", classes=60, **kw) -> ArchSpec:
     return ArchSpec(stgcn_blocks(strided=False), padding=0, skeleton=skeleton, classes=classes, **kw)
 
 
+def coa_gcn_arch(skeleton="ntu", classes=60, **kw) -> ArchSpec:
+    """CoA-GCN: the CoST-GCN geometry with AdaptiveGraphConvolution (models/coa_gcn/coa_gcn.py:17-46)."""
+    return ArchSpec(stgcn_blocks(strided=True), padding=4, skeleton=skeleton, classes=classes, graph_conv="adaptive", **kw)
+
+
 def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
@@ -122,6 +128,11 @@ def make_state_dict(arch: ArchSpec, seed: int, randomize: bool = False) -> "Orde
         sd[g + "A"] = _t(A)
         for i in range(3):
             _conv(rng, sd, g + f"g_conv.{i}.", b.cout, b.cin, 1, bs=3)
+        if arch.graph_conv == "adaptive":  # a_gcn.py:14,25-31 (coff_embedding = 4)
+            inter_c = b.cout // 4
+            for i in range(3):
+                _conv(rng, sd, g + f"a_conv.{i}.", inter_c, b.cin, 1, bs=1)
+                _conv(rng, sd, g + f"b_conv.{i}.", inter_c, b.cin, 1, bs=1)
         if b.cin != b.cout:
             _conv(rng, sd, g + "gcn_residual.0.", b.cout, b.cin, 1, bs=1)
             _bn(sd, g + "gcn_residual.1.", b.cout, 1)

@@ -187,3 +187,21 @@ def test_host_schedule_of_a_strided_stack():
                 ref.forward_step(x)
         stack = cs.CoStack([cs.BlockSpec(b.cin, b.cout, b.stride, b.residual) for b in blocks], padding=pad)
         assert stack.simulate_schedule(60) == [tuple(f) for f in ref.trace]
+
+
+def test_aggregate_preds_matches_numpy_reduction():
+    """scripts/multi_stream_eval.py:33-42: reduce with np.add / np.maximum, equal shapes required."""
+    import numpy as np
+    import torch
+
+    import continual_skeletons_b200 as cs
+
+    rng = np.random.default_rng(0)
+    preds = [rng.standard_normal((6, 60)).astype(np.float32) for _ in range(3)]
+    tp = [torch.from_numpy(p) for p in preds]
+    np.testing.assert_array_equal(cs.aggregate_preds(tp, "add").numpy(), (preds[0] + preds[1]) + preds[2])
+    np.testing.assert_array_equal(cs.aggregate_preds(tp, "max").numpy(), np.maximum(np.maximum(preds[0], preds[1]), preds[2]))
+    with pytest.raises(ValueError):
+        cs.aggregate_preds([tp[0], tp[1][:3]])
+    with pytest.raises(ValueError):
+        cs.aggregate_preds(tp, "mean")

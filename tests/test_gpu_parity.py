@@ -269,3 +269,35 @@ def test_merged_launch_matches_separate_kernels(monkeypatch):
         outs[merge + "n"] = m.launch_count() - launches0
     assert outs["1n"] < outs["0n"], "the merged path did not run"
     assert torch.equal(outs["0"], outs["1"])
+
+
+def test_benchmark_script_semantics():
+    """scripts/benchmark_all_ntu60.py: warm-up then one prediction per stream on every timed call of `stride` frames."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "benchmark_all_ntu60.py")
+    spec = importlib.util.spec_from_file_location("benchmark_all_ntu60", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, frames in (("cost_gcn", 4), ("cost_gcn_mod", 1)):
+        r = mod.profile_model(name, 8, 3, "dummy_ntu", torch.device(DEV))
+        assert r["frames_per_prediction"] == frames and r["predictions_per_s"] > 0
+
+
+def test_multi_stream_fusion_on_device():
+    """Two lock-stepped models (joint / bone modality): fused logits == sum of the members' own logits."""
+    import continual_skeletons_b200 as cs
+
+    torch.manual_seed(3)
+    members = [cs.CoStGcn({"dataset_name": "dummy_ntu"}) for _ in range(2)]
+    solo = [cs.CoStGcn({"dataset_name": "dummy_ntu"}) for _ in range(2)]
+    for m, s in zip(members, solo):
+        s.load_state_dict(m.state_dict())
+    ens = cs.MultiStream(members, "add")
+    x = [torch.randn(2, 3, 300, 25, 2, device=DEV) for _ in range(2)]
+    fused = ens.forward_steps(x)
+    want = solo[0].forward_steps(x[0]) + solo[1].forward_steps(x[1])
+    assert fused is not None and torch.equal(fused, want)
+    ens.clean_state()
+    assert ens.forward_step([x[0][:, :, 0], x[1][:, :, 0]]) is None

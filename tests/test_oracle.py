@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import graphs, ref_shim, regular, step, weights
-from oracle.make_golden import BLOCK_B, BLOCK_CASES, BLOCK_T
+from oracle.make_golden import ADAPTIVE_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
 from oracle.weights import ArchSpec, BlockSpec
 
 
@@ -169,3 +169,77 @@ def test_step_oracle_kinetics_graph():
     n = out.shape[2]
     assert n == target.shape[2] - arch.stack_padding // arch.stack_stride
     assert torch.allclose(out, target[:, :, :n], atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# CoA-GCN: AdaptiveGraphConvolution evaluated one frame at a time
+# ---------------------------------------------------------------------------------------------
+def _adaptive_case(idx, rnd):
+    name, cin, cout, stride, residual, pad = ADAPTIVE_BLOCK_CASES[idx]
+    arch = ArchSpec([BlockSpec(cin, cout, stride, residual)], padding=pad, head=False, block_names=[""], graph_conv="adaptive")
+    sd = weights.make_state_dict(arch, seed=3000 + idx, randomize=rnd)
+    wide = "wide" in name
+    x = weights.make_input((1 if wide else BLOCK_B, cin, 14 if wide else BLOCK_T, 25), seed=4000 + idx)
+    return name + ("_rnd" if rnd else ""), arch, sd, x
+
+
+@pytest.mark.parametrize("idx", range(len(ADAPTIVE_BLOCK_CASES)))
+@pytest.mark.parametrize("rnd", [False, True])
+def test_adaptive_block_vs_golden(golden, idx, rnd):
+    """Clip-layout restatement with per-frame attention, and the step oracle, against the reference's own
+    AdaptiveGraphConvolution + SpatioTemporalBlock (fixtures by oracle/make_golden.py)."""
+    key, arch, sd, x = _adaptive_case(idx, rnd)
+    spec, p = arch.blocks[0], arch.padding
+    ref = torch.from_numpy(golden["coa_blocks"][key])
+    scale = max(1.0, float(ref.abs().max()))
+    y = regular.st_block(x, sd, "", spec, p, per_frame=True)
+    assert y.shape == ref.shape and torch.allclose(y, ref, atol=2e-6 * scale)
+    g = regular.graph_conv(x[:, :, :2], sd, "gcn.", per_frame=True)
+    assert torch.allclose(g, torch.from_numpy(golden["coa_blocks"][key + "_gcn"]), atol=2e-6 * scale)
+    blk = step.StepBlock(sd, "", spec, p)
+    emitted = [o for o in (blk.step(x[:, :, t]) for t in range(x.shape[2])) if o is not None]
+    assert len(emitted) == (x.shape[2] - (8 - p) + spec.stride - 1) // spec.stride
+    for j, o in enumerate(emitted):
+        assert torch.allclose(o, ref[:, :, j], atol=2e-6 * scale), (key, j)
+
+
+def test_adaptive_attention_spans_the_clip():
+    """The reason CoA-GCN is not equivalent to A-GCN (models/coa_gcn/coa_gcn.py:29): over a clip the reference
+    normalises one attention map over all frames, per step it sees one frame."""
+    key, arch, sd, x = _adaptive_case(1, True)
+    whole = regular.graph_conv(x, sd, "gcn.")
+    framewise = regular.graph_conv(x, sd, "gcn.", per_frame=True)
+    assert whole.shape == framewise.shape and not torch.allclose(whole, framewise, atol=1e-3)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_adaptive_graph_conv_vs_live_reference():
+    ref = ref_shim.load()
+    for idx in (1, 5):
+        key, arch, sd, x = _adaptive_case(idx, True)
+        b = arch.blocks[0]
+        gc = ref.AdaptiveGraphConvolution(b.cin, b.cout, ref.ntu_A)
+        gc.load_state_dict({k[len("gcn."):]: v for k, v in sd.items() if k.startswith("gcn.")}, strict=True)
+        gc.eval()
+        with torch.no_grad():
+            assert torch.allclose(regular.graph_conv(x, sd, "gcn."), gc(x), atol=1e-6)  # whole-clip attention
+            assert torch.allclose(regular.graph_conv(x[:, :, 3:4], sd, "gcn."), gc(x[:, :, 3:4]), atol=1e-6)
+
+
+@pytest.mark.parametrize("rnd", [False, True])
+def test_step_model_coa_gcn(golden, rnd):
+    """CoAGcn steps: same schedule as CoStGcn (first logits at frame 296), logits equal to the reference blocks
+    run with per-frame attention."""
+    g, sfx = golden["coa_gcn"], "_rnd" if rnd else ""
+    arch = weights.coa_gcn_arch()
+    assert (arch.receptive_field, arch.stack_stride, arch.stack_padding, arch.pool_size, arch.pool_padding) == (153, 4, 76, 75, 19)
+    sd = weights.make_state_dict(arch, seed=8 if rnd else 7, randomize=rnd)
+    x = weights.make_input((2, 3, 300, 25, 2), seed=11)
+    m = step.StepModel(sd, arch)
+    with torch.no_grad():
+        out = m.forward_steps(x)
+    assert out.shape == (2, 60)
+    assert [i for i, f in enumerate(m.trace) if f[-1]] == [296]
+    co = torch.from_numpy(g["coa_gcn_co_logits" + sfx])
+    scale = max(1.0, float(co.abs().max()) / 16)
+    assert torch.allclose(out, co, rtol=1e-4, atol=1e-4 * scale)
