@@ -154,7 +154,12 @@ def make_state_dict(arch: ArchSpec, seed: int, randomize: bool = False) -> "Orde
                 continue
             is_bn = (k[: k.rfind(".")] + ".running_var") in sd
             if k.endswith("graph_attn"):
-                sd[k] = _t(rng.uniform(0.5, 1.5, size=tuple(v.shape)))
+                if arch.graph_conv == "adaptive":
+                    # dense additive term (a_gcn.py:50): keep it small so that ten layers of it do not blow the
+                    # activations up to where every attention softmax saturates into a hard arg-max
+                    sd[k] = _t(rng.uniform(-0.04, 0.08, size=tuple(v.shape)))
+                else:
+                    sd[k] = _t(rng.uniform(0.5, 1.5, size=tuple(v.shape)))
             elif k.endswith("running_var"):
                 sd[k] = _t(rng.uniform(0.5, 1.5, size=tuple(v.shape)))
             elif k.endswith("running_mean"):
