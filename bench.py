@@ -32,8 +32,11 @@ V, S, C_IN, CLASSES = 25, 2, 3, 60
 ALGO = {
     "cost_gcn": {"state": 1.408e6, "io": 600 + 240 / 4 + 2048 / 4, "flops": 115.0e6, "warm": 297, "period": 4},
     "cost_gcn_mod": {"state": 3.072e6, "io": 600 + 240 + 2048, "flops": 318.0e6, "warm": 300, "period": 1},
+    # CoA-GCN: same rings and schedule as CoST-GCN; FLOPs scaled by the paper's
+    # per-prediction costs, 0.30 G vs 0.27 G (figures/table-2.png)
+    "coa_gcn": {"state": 1.408e6, "io": 600 + 240 / 4 + 2048 / 4, "flops": 115.0e6 * 0.30 / 0.27, "warm": 297, "period": 4},
 }
-NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*"}
+NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*", "coa_gcn": "CoA-GCN"}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches
 # listed in profiles/r1h_dram_bytes_per_launch.csv (ncu, --cache-control none); None where no capture exists.
 NCU_TRAFFIC = {"tcn<64>": 565.0e6, "tcn<128>": 1136.0e6, "tcn<256>": 2322.0e6, "gcn<64>": 68.0e6, "gcn<128>": 146.0e6,
@@ -99,7 +102,7 @@ def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    arch = weights.cost_gcn_arch() if workload == "cost_gcn" else weights.cost_gcn_mod_arch()
+    arch = {"cost_gcn": weights.cost_gcn_arch, "cost_gcn_mod": weights.cost_gcn_mod_arch, "coa_gcn": weights.coa_gcn_arch}[workload]()
     sd = weights.make_state_dict(arch, seed=0)
     model = step.StepModel(sd, arch)
     frames = [torch.rand(n_streams, C_IN, V, S) for _ in range(4)]
@@ -126,7 +129,7 @@ def run_reference(args, rank, world):
     sample = (f"{n_sample} concurrent streams per step (bounded sample of the {args.streams}-stream workload), steady state "
               f"after {ALGO[args.workload]['warm']} warm frames, oracle/step.py eager torch fp32")
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "p50_ms_per_step": p50, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -162,7 +165,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     algo = ALGO[args.workload]
-    cls = cs.CoStGcn if args.workload == "cost_gcn" else cs.CoStGcnMod
+    cls = {"cost_gcn": cs.CoStGcn, "cost_gcn_mod": cs.CoStGcnMod, "coa_gcn": cs.CoAGcn}[args.workload]
     torch.manual_seed(0)
     model = cls({"dataset_name": "dummy_ntu", "forward_mode": "frame", "kernel_path": args.kernel_path})
     n_local = args.streams
@@ -306,7 +309,7 @@ def run_ours(args, rank, world, local_rank):
     traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 else None
     step_bytes = algo["state"] + algo["io"]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, f32 accumulate)" if args.kernel_path == "auto" else "f32",
         "data": "synthetic", "config": make_config(args, world),

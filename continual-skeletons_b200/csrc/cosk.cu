@@ -41,11 +41,12 @@ struct ActBuf {  // token-major split-bf16 activation ring: [slots][plane hi/lo]
 
 struct BlockW {
   // host copies as loaded (BN already folded by the caller)
-  std::vector<float> mix, gcn_w, gcn_b, tcn_w, res_w, tcn_b;
+  std::vector<float> mix, gcn_w, gcn_b, tcn_w, res_w, tcn_b, att_w, att_b;
   // device, SIMT format (k-major fp32)
   float *d_gcn_w = nullptr, *d_gcn_b = nullptr, *d_tcn_w = nullptr, *d_res_w = nullptr, *d_tcn_b = nullptr;
   int *d_mix_ptr = nullptr, *d_mix_src = nullptr;
   float *d_mix_val = nullptr;
+  float *d_att_w = nullptr, *d_att_b = nullptr, *d_adj = nullptr;  // adaptive graph conv: k-major embedding convs, dense A + graph_attn
   int mix_max_nz = 0;
   int gcn_parts = 4;  // accumulator column groups of the tensor-core graph conv (3 or 4)
   int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
@@ -94,6 +95,8 @@ struct cosk_model {
   ActBuf xin;
   float *d_pool_ring = nullptr;
   double *d_pool_sum = nullptr;
+  float *d_dense = nullptr;  // adaptive graph conv: per-token mixing rows [t_alloc][3][dense_vp] of the frame in flight
+  int dense_vp = 0;
   long long pool_n = 0, frame = 0;
   std::vector<int32_t> last_flags;
   unsigned int *d_dbg = nullptr;
@@ -142,6 +145,7 @@ void free_state(cosk_model *m) {
   }
   dfree(m->d_pool_ring);
   dfree(m->d_pool_sum);
+  dfree(m->d_dense);
   m->n_streams = 0;
   m->state_bytes = 0;
 }
@@ -249,6 +253,12 @@ int prepare(cosk_model *m) {
     if (b.tcn_b.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.tcn.b missing", i);
     if (bc.res_kind == COSK_RES_CONV && b.res_w.size() != (size_t)bc.cout * bc.cin)
       return fail(m, COSK_ERR_STATE, "block%d.res.w missing", i);
+    const bool adaptive = c.graph_conv == COSK_GCONV_ADAPTIVE;
+    if (adaptive) {
+      const int ic = bc.cout / 4;  // coff_embedding = 4, models/a_gcn/a_gcn.py:13-14
+      if (b.att_w.size() != (size_t)6 * ic * bc.cin || b.att_b.size() != (size_t)6 * ic)
+        return fail(m, COSK_ERR_STATE, "block%d.att.w / att.b missing or wrong size", i);
+    }
     // CSR of A * graph_attn over (partition, output vertex)
     std::vector<int> ptr(3 * V + 1, 0), src;
     std::vector<float> val;
@@ -293,9 +303,15 @@ int prepare(cosk_model *m) {
       t = transpose(b.res_w.data(), bc.cout, bc.cin);
       if ((rc = upload(m, b.d_res_w, t.data(), t.size()))) return rc;
     }
+    if (adaptive) {
+      t = transpose(b.att_w.data(), 6 * (bc.cout / 4), bc.cin);
+      if ((rc = upload(m, b.d_att_w, t.data(), t.size()))) return rc;
+      if ((rc = upload(m, b.d_att_b, b.att_b.data(), b.att_b.size()))) return rc;
+      if ((rc = upload(m, b.d_adj, b.mix.data(), b.mix.size()))) return rc;
+    }
     // tensor-core eligibility + weights
     const bool want_tc = c.path == COSK_PATH_AUTO;
-    b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
+    b.tc_gcn = want_tc && !adaptive && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
     b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
     if (b.tc_gcn) {
       // Rows regrouped per pass of 64 output channels: row = pass*(P*64) + part*64 + c, K = cin.
@@ -419,6 +435,7 @@ int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
 }
 
 int set_smem_attrs(cosk_model *m) {
+  CK(cudaFuncSetAttribute(k_agcn_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMaxSmem));
   CK(cudaFuncSetAttribute(k_tc_tcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<256>::kSmemBytes));
@@ -557,6 +574,27 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
   const int res_conv = bc.cin != bc.cout ? 1 : 0;
   int rc = prof_mark(m, 1, i, s);
   if (rc) return rc;
+  const bool adaptive = m->cfg.graph_conv == COSK_GCONV_ADAPTIVE;
+  if (adaptive) {
+    // attention half: the per-token mixing rows of this frame go to the dense scratch
+    AttnArgs t;
+    t.x_hi = in.hi(in_slot);
+    t.x_lo = in.lo(in_slot);
+    t.cs_in = in.cs;
+    t.cin = bc.cin;
+    t.w = b.d_att_w;
+    t.bias = b.d_att_b;
+    t.inter_c = bc.cout / 4;
+    t.adj = b.d_adj;
+    t.V = m->cfg.vertices;
+    t.n_tokens = m->n_tokens;
+    t.tile_tokens = m->tile_tokens;
+    t.dense = m->d_dense;
+    t.dense_ld = 3 * m->dense_vp;
+    t.dense_vp = m->dense_vp;
+    CK(launch_k(m, k_agcn_attn, dim3(m->n_tiles), dim3(256), (size_t)2 * t.inter_c * kTileRows * sizeof(float), s, t));
+    m->launches++;
+  }
   if (b.tc_gcn) {
     TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
     // one K-block per work item (cin = 64): single operand stage, four exchange buffers
@@ -584,6 +622,9 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     a.V = m->cfg.vertices;
     a.n_tokens = m->n_tokens;
     a.tile_tokens = m->tile_tokens;
+    a.dense = adaptive ? m->d_dense : nullptr;
+    a.dense_ld = 3 * m->dense_vp;
+    a.dense_vp = m->dense_vp;
     const int K = (3 + res_conv) * bc.cin;
     if (bc.cin <= 8 && res_conv && bc.cout % 32 == 0 && K <= kSmallKMax && m->cfg.path == COSK_PATH_AUTO) {
       CK(launch_k(m, k_gcn_small, dim3(m->n_tiles), dim3(256), (size_t)(K + 1) * bc.cout * sizeof(float), s, a));
@@ -759,6 +800,8 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (cfg->n_blocks < 1 || cfg->n_blocks > COSK_MAX_BLOCKS) return COSK_ERR_ARG;
   if (cfg->vertices < 1 || cfg->vertices > kTileRows || cfg->persons < 1 || cfg->c_in < 1) return COSK_ERR_ARG;
   if (cfg->padding != 0 && cfg->padding != 4) return COSK_ERR_ARG;
+  if (cfg->graph_conv != COSK_GCONV_PLAIN && cfg->graph_conv != COSK_GCONV_ADAPTIVE) return COSK_ERR_ARG;
+  if (cfg->graph_conv == COSK_GCONV_ADAPTIVE && cfg->vertices > kAttnMaxV) return COSK_ERR_ARG;
   if (cfg->classes > 0 && (cfg->pool_size < 1 || cfg->pool_padding < 0 || cfg->pool_padding >= cfg->pool_size))
     return COSK_ERR_ARG;
   int prev = cfg->c_in;
@@ -767,6 +810,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
     if (b.cin != prev || b.cout < 1 || (b.stride != 1 && b.stride != 2)) return COSK_ERR_ARG;
     if (b.res_kind == COSK_RES_IDENTITY && (b.cin != b.cout || b.stride != 1)) return COSK_ERR_ARG;
     if (b.res_kind < 0 || b.res_kind > 2) return COSK_ERR_ARG;
+    if (cfg->graph_conv == COSK_GCONV_ADAPTIVE && (b.cout < 4 || b.cout / 4 > kAttnMaxInter)) return COSK_ERR_ARG;
     prev = b.cout;
   }
   cosk_model *m = new cosk_model();
@@ -838,6 +882,9 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_mix_ptr);
     dfree(b.d_mix_src);
     dfree(b.d_mix_val);
+    dfree(b.d_att_w);
+    dfree(b.d_att_b);
+    dfree(b.d_adj);
     dfree(b.d_gcn_w16);
     dfree(b.d_tcn_w16);
   }
@@ -873,6 +920,8 @@ int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t
     else if (f == "tcn.w") b.tcn_w = v;
     else if (f == "res.w") b.res_w = v;
     else if (f == "tcn.b") b.tcn_b = v;
+    else if (f == "att.w") b.att_w = v;
+    else if (f == "att.b") b.att_b = v;
     else return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
   } else {
     return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
@@ -911,6 +960,13 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
     CK(cudaMalloc(&m->d_pool_ring, (size_t)c.pool_size * n_streams * cl * sizeof(float)));
     CK(cudaMalloc(&m->d_pool_sum, (size_t)n_streams * cl * sizeof(double)));
     m->state_bytes += (int64_t)((size_t)c.pool_size * n_streams * cl * sizeof(float) + (size_t)n_streams * cl * sizeof(double));
+  }
+  if (c.graph_conv == COSK_GCONV_ADAPTIVE) {
+    m->dense_vp = round_up(c.vertices, 4);
+    const size_t bytes = (size_t)m->t_alloc * 3 * m->dense_vp * sizeof(float);
+    CK(cudaMalloc(&m->d_dense, bytes));
+    CK(cudaMemset(m->d_dense, 0, bytes));
+    m->state_bytes += (int64_t)bytes;  // scratch, not state, but part of the per-stream footprint
   }
   rc = zero_state(m, 0);
   if (rc) return rc;

@@ -109,6 +109,10 @@ struct GcnArgs {
   int V;
   long long n_tokens;
   int tile_tokens;
+  // adaptive graph conv: per-token dense mixing rows written by k_agcn_attn replace the CSR above;
+  // row of output token w, partition p, source vertex v: dense[w*dense_ld + p*dense_vp + v]
+  const float *dense;
+  int dense_ld, dense_vp;
 };
 
 // Graph convolution of one frame: z = sum_i W_i (x A_i) ; BN ; + gcn_residual(x) ; ReLU
@@ -147,12 +151,21 @@ __global__ void __launch_bounds__(256) k_gcn_simt(GcnArgs a) {
         if (row < rows_valid) {
           const int wv = row % a.V;
           const int sk0 = row - wv;
-          const int e1 = a.mix_ptr[part * a.V + wv + 1];
-          for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) {
-            const int src = sk0 + a.mix_src[e];
-            const float coef = a.mix_val[e];
+          if (a.dense != nullptr) {
+            const float *dm = a.dense + (tok0 + row) * a.dense_ld + part * a.dense_vp;
+            for (int v = 0; v < a.V; ++v) {
+              const float coef = dm[v];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) m[j] = fmaf(coef, Xs[half + j][src], m[j]);
+              for (int j = 0; j < 8; ++j) m[j] = fmaf(coef, Xs[half + j][sk0 + v], m[j]);
+            }
+          } else {
+            const int e1 = a.mix_ptr[part * a.V + wv + 1];
+            for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) {
+              const int src = sk0 + a.mix_src[e];
+              const float coef = a.mix_val[e];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) m[j] = fmaf(coef, Xs[half + j][src], m[j]);
+            }
           }
         }
 #pragma unroll
@@ -218,8 +231,13 @@ __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
     if (r < rows_valid) {
       if (part < 3) {
         const int wv = r % a.V, sk0 = r - wv;
-        const int e1 = a.mix_ptr[part * a.V + wv + 1];
-        for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) v = fmaf(a.mix_val[e], xs[sk0 + a.mix_src[e]][c], v);
+        if (a.dense != nullptr) {
+          const float *dm = a.dense + (tok0 + r) * a.dense_ld + part * a.dense_vp;
+          for (int sv = 0; sv < a.V; ++sv) v = fmaf(dm[sv], xs[sk0 + sv][c], v);
+        } else {
+          const int e1 = a.mix_ptr[part * a.V + wv + 1];
+          for (int e = a.mix_ptr[part * a.V + wv]; e < e1; ++e) v = fmaf(a.mix_val[e], xs[sk0 + a.mix_src[e]][c], v);
+        }
       } else {
         v = xs[r][c];
       }
@@ -262,6 +280,91 @@ __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
       *reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + n0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
       *reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + n0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adaptive graph conv, attention half (AdaptiveGraphConvolution.forward with T = 1, models/a_gcn/a_gcn.py:52-63):
+// per skeleton and partition i
+//     S_i[v][w] = sum_c theta_i[c][v] * phi_i[c][w] / inter_c ,  theta_i = a_conv_i(x), phi_i = b_conv_i(x)
+//     M_i[v][w] = softmax over v of S_i[.][w]  +  (A + graph_attn)_i[v][w]
+// and the mixing row of every output token w is written to the dense scratch the graph-conv kernels read.
+// fp32 CUDA-core version (any channel count): one token tile per CTA.
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const __nv_bfloat16 *x_hi, *x_lo;
+  int cs_in, cin;
+  const float *w;     // [cin][6*inter_c] k-major: columns theta_0 | phi_0 | theta_1 | phi_1 | theta_2 | phi_2
+  const float *bias;  // [6*inter_c]
+  int inter_c;
+  const float *adj;   // [3][V][V] static term A + graph_attn
+  int V;
+  long long n_tokens;
+  int tile_tokens;
+  float *dense;
+  int dense_ld, dense_vp;
+};
+
+constexpr int kAttnMaxV = 32;
+constexpr int kAttnMaxInter = 64;                                      // inter_c of a 256-channel block
+constexpr int kAttnMaxSmem = 2 * kAttnMaxInter * kTileRows * 4;        // dynamic shared memory of k_agcn_attn
+
+__global__ void __launch_bounds__(256) k_agcn_attn(AttnArgs a) {
+  __shared__ __align__(16) float Xs[kSimtK][kTileRows];
+  __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  extern __shared__ __align__(16) float tp[];  // [2*inter_c][kTileRows]: theta rows, then phi rows, of one partition
+  pdl_trigger();
+  pdl_wait();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  const int ic = a.inter_c, ld = 6 * ic;
+  for (int part = 0; part < 3; ++part) {
+    for (int n0 = 0; n0 < 2 * ic; n0 += kSimtN) {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int c0 = 0; c0 < a.cin; c0 += kSimtK) {
+        __syncthreads();
+        simt_load_rows(Xs, a.x_hi, a.x_lo, a.cs_in, c0, a.cin, tok0, rows_valid);
+        simt_load_w(Bs, a.w, ld, c0, min(kSimtK, a.cin - c0), part * 2 * ic + n0, (part + 1) * 2 * ic);
+        __syncthreads();
+        simt_mma_chunk(acc, Xs, Bs, ty, tx);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n >= 2 * ic) continue;
+        const float b = a.bias[part * 2 * ic + n];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tp[n * kTileRows + ty * 8 + i] = acc[i][j] + b;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < rows_valid) {
+      const int row = threadIdx.x;
+      const int wv = row % a.V, sk0 = row - wv;
+      float sv[kAttnMaxV];
+      float mx = -INFINITY;
+      for (int v = 0; v < a.V; ++v) {
+        float d = 0.f;
+        for (int c = 0; c < ic; ++c) d = fmaf(tp[c * kTileRows + sk0 + v], tp[(ic + c) * kTileRows + row], d);
+        d = d / (float)ic;
+        sv[v] = d;
+        mx = fmaxf(mx, d);
+      }
+      float sum = 0.f;
+      for (int v = 0; v < a.V; ++v) {
+        sv[v] = expf(sv[v] - mx);
+        sum += sv[v];
+      }
+      float *dst = a.dense + (tok0 + row) * a.dense_ld + part * a.dense_vp;
+      for (int v = 0; v < a.V; ++v) dst[v] = sv[v] / sum + a.adj[((size_t)part * a.V + v) * a.V + wv];
+    }
+    __syncthreads();
   }
 }
 

@@ -111,6 +111,21 @@ def _gcn_params(cin, cout, A):
     return g
 
 
+def _agcn_params(cin, cout, A, coff_embedding=4):
+    """Parameters of AdaptiveGraphConvolution (models/a_gcn/a_gcn.py:13-46): the plain graph conv's tensors plus
+    the two embedding convs per partition; ``graph_attn`` is an additive dense term initialised to 1."""
+    g = _gcn_params(cin, cout, A)
+    inter_c = cout // coff_embedding
+    if inter_c < 1:
+        raise ValueError("AdaptiveGraphConvolution needs out_channels >= 4")
+    g.a_conv = nn.ModuleList(nn.Conv2d(cin, inter_c, 1) for _ in range(3))
+    g.b_conv = nn.ModuleList(nn.Conv2d(cin, inter_c, 1) for _ in range(3))
+    for conv in list(g.a_conv) + list(g.b_conv):
+        _init_conv(conv, 1)
+    g.inter_c = inter_c
+    return g
+
+
 def _tconv_params(cin, cout, k, stride, pad):
     """Parameters of (Co)TemporalConvolution (models/base.py:279-334)."""
     t = _Node()
@@ -121,11 +136,11 @@ def _tconv_params(cin, cout, k, stride, pad):
     return t
 
 
-def _block_params(spec, A, pad):
+def _block_params(spec, A, pad, adaptive=False):
     """Module tree with the state_dict keys of CoSpatioTemporalBlock (models/base.py:412-446):
     plain ``gcn.* / tcn.*`` without residual, ``0.1.gcn.* / 0.1.tcn.*`` under a residual wrapper,
     plus ``0.0.residual.*`` for the strided 1x1 residual conv."""
-    gcn = _gcn_params(spec.cin, spec.cout, A)
+    gcn = (_agcn_params if adaptive else _gcn_params)(spec.cin, spec.cout, A)
     tcn = _tconv_params(spec.cout, spec.cout, KT, spec.stride, pad)
     blk = _Node()
     if spec.res_kind == 0:
@@ -161,11 +176,18 @@ def _folded_block_tensors(blk, spec):
         sr, tr = _fold_bn(gcn.gcn_residual[1])
         ws.append(gcn.gcn_residual[0].weight.detach().double()[:, :, 0, 0] * sr[:, None])
         bias = bias + sr * gcn.gcn_residual[0].bias.detach().double() + tr
+    adaptive = hasattr(gcn, "a_conv")
     out = {
-        "mix": (gcn.A.detach().double() * gcn.graph_attn.detach().double()),
+        # models/base.py:262 masks A with graph_attn; models/a_gcn/a_gcn.py:50 adds it
+        "mix": (gcn.A.detach().double() + gcn.graph_attn.detach().double()) if adaptive
+        else (gcn.A.detach().double() * gcn.graph_attn.detach().double()),
         "gcn.w": torch.cat(ws, dim=1),
         "gcn.b": bias,
     }
+    if adaptive:  # rows: theta_0, phi_0, theta_1, phi_1, theta_2, phi_2 (a_gcn.py:53-60)
+        convs = [c for pair in zip(gcn.a_conv, gcn.b_conv) for c in pair]
+        out["att.w"] = torch.cat([c.weight.detach().double()[:, :, 0, 0] for c in convs], dim=0)
+        out["att.b"] = torch.cat([c.bias.detach().double() for c in convs], dim=0)
     s, t = _fold_bn(tcn.bn)
     w = tcn.t_conv.weight.detach().double()[:, :, :, 0].permute(0, 2, 1) * s[:, None, None]  # [cout][tap][cin]
     out["tcn.w"] = w.reshape(spec.cout, KT * spec.cout)
@@ -223,7 +245,8 @@ class _Engine:
 class _CoBase(nn.Module):
     """Shared machinery of the full models and the headless block stack."""
 
-    def _setup(self, specs, pad, V, S, c_in, classes, head, A, path):
+    def _setup(self, specs, pad, V, S, c_in, classes, head, A, path, adaptive=False):
+        self._adaptive = bool(adaptive)
         self._specs, self._pad, self._V, self._S, self._c_in = list(specs), int(pad), int(V), int(S), int(c_in)
         self._classes, self._head, self._path = int(classes), bool(head), path
         self._engine, self._dirty, self._shape = None, True, None
@@ -246,6 +269,7 @@ class _CoBase(nn.Module):
         cfg.pool_size, cfg.pool_padding = (self.pool_size, self.pool_padding) if self._head else (0, 0)
         cfg.data_bn = 1 if self._head else 0
         cfg.path = {"auto": 0, "simt": 1}[self._path]
+        cfg.graph_conv = 1 if self._adaptive else 0
         for i, sp in enumerate(self._specs):
             cfg.blocks[i].cin, cfg.blocks[i].cout = sp.cin, sp.cout
             cfg.blocks[i].stride, cfg.blocks[i].res_kind = sp.stride, sp.res_kind
@@ -416,6 +440,7 @@ class CoModelBase(_CoBase):
 
     PADDING = 4
     STRIDED = True
+    ADAPTIVE = False  # AdaptiveGraphConvolution instead of GraphConvolution (CoAGcn)
 
     @staticmethod
     def configs():
@@ -461,13 +486,13 @@ class CoModelBase(_CoBase):
         self.output_shape = (classes,)
         self.num_classes = classes
         specs = self.block_specs(c_in)
-        self._setup(specs, self.PADDING, V, S, c_in, classes, True, self.graph.A, self.hparams.kernel_path)
+        self._setup(specs, self.PADDING, V, S, c_in, classes, True, self.graph.A, self.hparams.kernel_path, self.ADAPTIVE)
 
         self.data_bn = nn.BatchNorm1d(S * c_in * V)
         _init_bn(self.data_bn, 1)
         self.layers = _Node()
         for i, sp in enumerate(specs):
-            self.layers.add_module(f"layer{i + 1}", _block_params(sp, self.graph.A, self.PADDING))
+            self.layers.add_module(f"layer{i + 1}", _block_params(sp, self.graph.A, self.PADDING, self.ADAPTIVE))
         self.fc = nn.Linear(256, classes)
         nn.init.normal_(self.fc.weight, 0, math.sqrt(2.0 / classes))  # models/utils.py:23-24
 
@@ -567,6 +592,13 @@ class CoStGcnMod(CoModelBase):
     PADDING, STRIDED = 0, False
 
 
+class CoAGcn(CoModelBase):
+    """CoA-GCN: the CoST-GCN geometry with ``AdaptiveGraphConvolution`` stepped one frame at a time
+    (models/coa_gcn/coa_gcn.py:11-46; the vertex attention of a step sees that step's frame only)."""
+
+    PADDING, STRIDED, ADAPTIVE = 4, True, True
+
+
 # ---------------------------------------------------------------------------------------------
 # headless stack of blocks (what the reference's block-level tests build with co.Sequential)
 # ---------------------------------------------------------------------------------------------
@@ -575,13 +607,13 @@ class CoStack(_CoBase):
     Children are named "0", "1", ... like ``continual.Sequential`` names them
     (tests/test_cost_gcn.py:288-312 in the reference)."""
 
-    def __init__(self, blocks, padding=4, skeleton="ntu", kernel_path="auto"):
+    def __init__(self, blocks, padding=4, skeleton="ntu", kernel_path="auto", adaptive=False):
         super().__init__()
         g = _graph.ntu_graph() if skeleton == "ntu" else _graph.kinetics_graph()
         specs = [b if isinstance(b, BlockSpec) else BlockSpec(*b) for b in blocks]
-        self._setup(specs, padding, g.num_node, 1, specs[0].cin, 0, False, g.A, kernel_path)
+        self._setup(specs, padding, g.num_node, 1, specs[0].cin, 0, False, g.A, kernel_path, adaptive)
         for i, sp in enumerate(specs):
-            self.add_module(str(i), _block_params(sp, g.A, padding))
+            self.add_module(str(i), _block_params(sp, g.A, padding, adaptive))
         self.eval()
 
     def _block_modules(self):

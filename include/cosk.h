@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 #define COSK_MAX_BLOCKS 16
-#define COSK_ABI_VERSION 1
+#define COSK_ABI_VERSION 2
 
 typedef struct cosk_model cosk_model;
 
@@ -42,6 +42,13 @@ enum cosk_res_kind { COSK_RES_NONE = 0, COSK_RES_IDENTITY = 1, COSK_RES_CONV = 2
 enum cosk_path {
   COSK_PATH_AUTO = 0, /* tcgen05 tile kernels wherever channels are multiples of 64, else SIMT */
   COSK_PATH_SIMT = 1  /* fp32 CUDA-core kernels everywhere: on-device checker, not the product */
+};
+
+/* graph convolution of every block */
+enum cosk_graph_conv {
+  COSK_GCONV_PLAIN = 0,   /* GraphConvolution: fixed sparse A * graph_attn (models/base.py:230-270) */
+  COSK_GCONV_ADAPTIVE = 1 /* AdaptiveGraphConvolution: dense A + graph_attn plus a per-frame softmax vertex attention
+                             (models/a_gcn/a_gcn.py:12-69, stepped by models/coa_gcn/coa_gcn.py:11-14) */
 };
 
 typedef struct {
@@ -66,6 +73,7 @@ typedef struct {
   int32_t data_bn;      /* 1: per-feature affine of data_bn (models/base.py:76) on the input */
   int32_t device;       /* CUDA device ordinal */
   int32_t path;         /* enum cosk_path */
+  int32_t graph_conv;   /* enum cosk_graph_conv */
   cosk_block_cfg blocks[COSK_MAX_BLOCKS];
 } cosk_config;
 
@@ -76,7 +84,10 @@ void cosk_destroy(cosk_model *m);
 /* Stands behind load_state_dict (models/base.py:200-227 mapping is done by the host side, which
  * also folds eval-mode BatchNorm into the preceding conv).  `name` is one of
  *   "data_bn.scale" "data_bn.shift"            [S*V*C]   feature f = s*V*C + v*C + c
- *   "block<i>.mix"                             [3][V][V] A * graph_attn (models/base.py:262)
+ *   "block<i>.mix"                             [3][V][V] A * graph_attn (models/base.py:262);
+ *                                              A + graph_attn for COSK_GCONV_ADAPTIVE (models/a_gcn/a_gcn.py:50)
+ *   "block<i>.att.w"  "block<i>.att.b"         [6*(cout/4)][cin], [6*(cout/4)]   COSK_GCONV_ADAPTIVE only: the embedding
+ *                                              convs, rows theta_0, phi_0, theta_1, phi_1, theta_2, phi_2 (a_gcn.py:53-60)
  *   "block<i>.gcn.w"                           [cout][3*cin (+cin if cin != cout)]  partition-major K
  *   "block<i>.gcn.b"                           [cout]
  *   "block<i>.tcn.w"                           [cout][9*cout]  tap-major K (tap 8 = newest frame)

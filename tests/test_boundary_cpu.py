@@ -32,15 +32,20 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header():
-    # 12 int32 fields + 16 blocks of 4 int32
-    assert ctypes.sizeof(cslib.Config) == 4 * (12 + 4 * cslib.MAX_BLOCKS)
+    # 13 int32 fields + 16 blocks of 4 int32
+    assert ctypes.sizeof(cslib.Config) == 4 * (13 + 4 * cslib.MAX_BLOCKS)
+    header = open(os.path.join(ROOT, "include", "cosk.h")).read()
+    body = header[header.index("typedef struct {\n  int32_t abi_version"): header.index("} cosk_config;")]
+    fields = re.findall(r"int32_t\s+(\w+);", body)
+    assert fields == [n for n, _ in cslib.Config._fields_[:-1]]
+    assert int(re.search(r"#define COSK_ABI_VERSION (\d+)", header).group(1)) == cslib.ABI_VERSION
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_fails_loudly_without_gpu():
     lib = cs.load_library()
     cfg = cslib.Config()
-    cfg.abi_version, cfg.vertices, cfg.persons, cfg.c_in, cfg.n_blocks, cfg.padding = 1, 25, 1, 4, 1, 4
+    cfg.abi_version, cfg.vertices, cfg.persons, cfg.c_in, cfg.n_blocks, cfg.padding = cslib.ABI_VERSION, 25, 1, 4, 1, 4
     cfg.blocks[0].cin, cfg.blocks[0].cout, cfg.blocks[0].stride, cfg.blocks[0].res_kind = 4, 4, 1, 0
     h = ctypes.c_void_p()
     assert lib.cosk_create(ctypes.byref(cfg), ctypes.byref(h)) == -2  # COSK_ERR_CUDA

@@ -14,7 +14,7 @@ import torch
 
 import continual_skeletons_b200 as cs
 from oracle import regular, step, weights
-from oracle.make_golden import BLOCK_B, BLOCK_CASES, BLOCK_T
+from oracle.make_golden import ADAPTIVE_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
 from oracle.weights import ArchSpec
 
 pytestmark = pytest.mark.gpu
@@ -301,3 +301,75 @@ def test_multi_stream_fusion_on_device():
     assert fused is not None and torch.equal(fused, want)
     ens.clean_state()
     assert ens.forward_step([x[0][:, :, 0], x[1][:, :, 0]]) is None
+
+
+# ---------------------------------------------------------------------------------------------
+# CoA-GCN: adaptive graph conv
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("rnd", [False, True])
+@pytest.mark.parametrize("idx", range(len(ADAPTIVE_BLOCK_CASES)))
+def test_adaptive_block_step_vs_golden(golden, idx, rnd, path):
+    """Block with AdaptiveGraphConvolution stepped frame by frame == the reference block with per-frame attention."""
+    name, cin, cout, stride, residual, pad = ADAPTIVE_BLOCK_CASES[idx]
+    arch = ArchSpec([weights.BlockSpec(cin, cout, stride, residual)], padding=pad, head=False, block_names=[""], graph_conv="adaptive")
+    sd = weights.make_state_dict(arch, seed=3000 + idx, randomize=rnd)
+    wide = "wide" in name
+    x = weights.make_input((1 if wide else BLOCK_B, cin, 14 if wide else BLOCK_T, 25), seed=4000 + idx)
+    spec = cs.BlockSpec(cin, cout, stride, residual)
+    stack = cs.CoStack([spec], padding=pad, kernel_path=path, adaptive=True)
+    stack.load_state_dict(_stack_keys(sd, spec), strict=True)
+    target = torch.from_numpy(golden["coa_blocks"][name + ("_rnd" if rnd else "")])
+    xd = x.to(DEV)
+    emitted = []
+    for t in range(x.shape[2]):
+        o = stack.forward_step(xd[:, :, t].contiguous())
+        due = t >= 8 - pad and (t - (8 - pad)) % stride == 0
+        assert (o is not None) == due, (name, t)
+        if o is not None:
+            emitted.append(o.cpu())
+    assert stack.device_error() == 0, hex(stack.device_error())
+    assert len(emitted) == (x.shape[2] - (8 - pad) + stride - 1) // stride  # no end padding: a prefix of the clip output
+    for j, o in enumerate(emitted):
+        assert _rel_err(o, target[:, :, j]) < BLOCK_RTOL, (name, rnd, path, j, _rel_err(o, target[:, :, j]))
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("rnd", [False, True])
+def test_coa_gcn_forward_steps_vs_reference(golden, rnd, path):
+    """CoAGcn.forward_steps over (2, 3, 300, 25, 2): one prediction at frame 296, logits as the reference blocks give."""
+    arch, sd, m = _load_model(cs.CoAGcn, weights.coa_gcn_arch, rnd, path)
+    x = weights.make_input((2, 3, 300, 25, 2), seed=11)
+    out = m.forward_steps(x.to(DEV))
+    assert m.device_error() == 0, hex(m.device_error())
+    assert out is not None and tuple(out.shape) == (2, 60)
+    out = out.cpu()
+    want = torch.from_numpy(golden["coa_gcn"]["coa_gcn_co_logits" + ("_rnd" if rnd else "")])
+    scale = max(1.0, float(want.abs().max()) / 16.0)
+    err = float((out - want).abs().max())
+    assert err <= 1e-3 * scale, (rnd, path, err, float(want.abs().max()))
+    assert torch.equal(out.argmax(1), want.argmax(1))
+
+
+def test_coa_gcn_schedule_and_blocks_vs_step_oracle():
+    arch, sd, m = _load_model(cs.CoAGcn, weights.coa_gcn_arch, True)
+    T = 60
+    x = weights.make_input((2, 3, T, 25, 2), seed=12)
+    ref = step.StepModel(sd, arch)
+    xd = x.to(DEV)
+    with torch.no_grad():
+        feats = []
+        regular.stack_features(regular.normalise_input(x, sd), sd, arch, feats, per_frame=True)
+    for t in range(T):
+        with torch.no_grad():
+            want = ref.forward_step(x[:, :, t])
+        got = m.forward_step(xd[:, :, t].contiguous())
+        assert m.last_schedule() == ref.trace[-1], t
+        assert (got is None) == (want is None)
+        if t in (30, 59):
+            for i in range(10):
+                n_out = sum(1 for f in ref.trace if f[i])
+                if n_out:
+                    e = _rel_err(m.read_block(i).cpu(), feats[i][:, :, n_out - 1])
+                    assert e < 2e-4, (t, i, e)
+    assert m.device_error() == 0
