@@ -81,6 +81,7 @@ struct cosk_model {
   int merge_min_tiles = 4 * 148;  // below this the two CTA groups are not worth splitting (COSK_MERGE_MIN_TILES)
   int merge_split64 = 100;  // CTAs given to the temporal-conv role (64-channel layers)
   int merge_split128 = 92;  // same for the 128-channel layers (CTA pairs)
+  int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
@@ -311,7 +312,10 @@ int prepare(cosk_model *m) {
     }
     // tensor-core eligibility + weights
     const bool want_tc = c.path == COSK_PATH_AUTO;
-    b.tc_gcn = want_tc && !adaptive && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
+    if (adaptive)  // dense-mix kernel: instantiated for the two skeleton sizes the reference ships
+      b.tc_gcn = want_tc && m->agcn_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && (V == 25 || V == 18);
+    else
+      b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
     b.tc_tcn = want_tc && tc_width(bc.cout) && (bc.res_kind != COSK_RES_CONV || bc.cin % kBK == 0);
     if (b.tc_gcn) {
       // Rows regrouped per pass of 64 output channels: row = pass*(P*64) + part*64 + c, K = cin.
@@ -319,7 +323,8 @@ int prepare(cosk_model *m) {
       // matrix (x = hi + lo passes through the split-precision products exactly).  The P = 3 variant of
       // the kernel (identity added from the input rows by the drain warps) exists but measured slower:
       // its row-per-thread global loads cost more load/store-unit cycles than the extra MMA columns.
-      const int P = b.gcn_parts = (res_conv || m->gcn_identity_mma) ? 4 : 3;
+      // (adaptive: 4 parts need the single-stage layout, so the identity rides along only when one K-block is all there is)
+      const int P = b.gcn_parts = adaptive ? ((res_conv || bc.cin == kBK) ? 4 : 3) : ((res_conv || m->gcn_identity_mma) ? 4 : 3);
       std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
       for (int o = 0; o < bc.cout; ++o)
         for (int part = 0; part < P; ++part) {
@@ -434,8 +439,19 @@ int launch_tc_gcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   return COSK_OK;
 }
 
+template <int P, int STAGES, int V>
+int launch_tc_agcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  CK(launch_k(m, k_tc_agcn<P, STAGES, V>, dim3(grid), dim3(512), TcAgcnCfg<P, STAGES>::kSmemBytes, s, args));
+  return COSK_OK;
+}
+
 int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_agcn_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMaxSmem));
+  CK(cudaFuncSetAttribute(k_tc_agcn<4, 1, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<4, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcn<3, 2, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<3, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcn<4, 1, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<4, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcn<3, 2, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<3, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<64>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<128>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTcnCfg<256>::kSmemBytes));
@@ -485,6 +501,9 @@ TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int
   a.epi.y_lo = b.ring.lo(ring_slot);
   a.epi.cs_out = b.ring.cs;
   a.dbg = m->d_dbg;
+  a.dense = m->d_dense;
+  a.dense_ld = 3 * m->dense_vp;
+  a.dense_vp = m->dense_vp;
   return a;
 }
 
@@ -595,7 +614,13 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     CK(launch_k(m, k_agcn_attn, dim3(m->n_tiles), dim3(256), (size_t)2 * t.inter_c * kTileRows * sizeof(float), s, t));
     m->launches++;
   }
-  if (b.tc_gcn) {
+  if (b.tc_gcn && adaptive) {
+    TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
+    const bool v25 = m->cfg.vertices == 25;
+    if (b.gcn_parts == 4) rc = v25 ? launch_tc_agcn<4, 1, 25>(m, a, s) : launch_tc_agcn<4, 1, 18>(m, a, s);
+    else rc = v25 ? launch_tc_agcn<3, 2, 25>(m, a, s) : launch_tc_agcn<3, 2, 18>(m, a, s);
+    if (rc) return rc;
+  } else if (b.tc_gcn) {
     TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
     // one K-block per work item (cin = 64): single operand stage, four exchange buffers
     const bool one_kb = bc.cin == kBK && m->gcn_single_stage;
@@ -829,6 +854,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
   if (const char *e = getenv("COSK_TCN_IDENTITY_MMA")) m->tcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_MERGE")) m->merge = atoi(e);
   if (const char *e = getenv("COSK_MERGE_MIN_TILES")) m->merge_min_tiles = atoi(e);

@@ -602,6 +602,10 @@ struct TcGcnArgs {
   unsigned int wait_need;        // the same launch: tile t may be loaded once wait_cnt[t] >= wait_need
   EpiArgs epi;                // r_hi/r_lo = input rows when cin == cout (identity gcn_residual, P = 3), else nullptr
   unsigned int *dbg;
+  // adaptive graph conv (k_tc_agcn): per-token dense mixing rows written by the attention kernel,
+  // dense[token*dense_ld + partition*dense_vp + source vertex]
+  const float *dense;
+  int dense_ld, dense_vp;
 };
 
 template <int P, int STAGES>
@@ -659,6 +663,93 @@ __device__ __forceinline__ void mix_gather(const uint8_t *buf, const uint32_t (&
       z[g].z = fmaf(cf[g][e], y[g][e].z, z[g].z);
       z[g].w = fmaf(cf[g][e], y[g][e].w, z[g].w);
     }
+  }
+}
+
+// TMA producer of the graph-conv kernels (one elected thread): per (tile, pass, K-block) the input tile rows
+// (hi, lo) and the [P*64 x 64] weight slab (hi, lo) of that pass.
+template <class Cfg, int P>
+__device__ __forceinline__ void gcn_producer(const TcGcnArgs &a, uint64_t *full, uint64_t *empty, const uint32_t smem_base,
+                                             const int cta, const int ncta) {
+  const int n_pass = a.cout / 64;
+  const int nkb = a.cin / kBK;
+  PipeState ps;
+  bool ok = true;
+  for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+    const int row = a.x_row + tile * a.tile_tokens;
+    if (a.wait_cnt != nullptr) {
+      // the input rows of this tile come from the temporal-conv role of the same launch
+      const long long t0 = clock64();
+      while (ptx::ld_acquire_u32(a.wait_cnt + tile) < a.wait_need) {
+        if (*(volatile unsigned int *)a.dbg != 0 || clock64() - t0 > ptx::kWaitLimitCycles) {
+          atomicCAS(a.dbg, 0u, kDbgTileFlag | (unsigned)(tile & 0xffffff));
+          ok = false;
+          break;
+        }
+        __nanosleep(200);
+      }
+      if (!ok) break;
+      ptx::fence_proxy_async_all();  // order the acquire (generic proxy) before the TMA reads (async proxy)
+    }
+    for (int pass = 0; ok && pass < n_pass; ++pass) {
+      for (int kc = 0; kc < nkb; ++kc) {
+        ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(pass * 16 + kc));
+        if (!ok) break;
+        const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
+        ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
+        // the input tile is re-read once per pass (L2 hits): keep it until the last pass, then let it go
+        const uint64_t xpol = pass + 1 < n_pass ? ptx::kEvictNormal : ptx::kEvictFirst;
+        ptx::tma_load_2d_hint(st, &a.tm_x, &full[ps.stage], kc * kBK, row, xpol);
+        ptx::tma_load_2d_hint(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc, xpol);
+        ptx::tma_load_2d_hint(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, pass * Cfg::kN, ptx::kEvictLast);
+        ptx::tma_load_2d_hint(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kc * kBK, P * a.cout + pass * Cfg::kN,
+                              ptx::kEvictLast);
+        ps.advance<Cfg::kStages>();
+      }
+    }
+  }
+}
+
+// MMA issuer of the graph-conv kernels (one elected thread): one accumulator of Cfg::kN columns per
+// (tile, pass), double buffered in TMEM.
+template <class Cfg, bool TRACE>
+__device__ __forceinline__ void gcn_mma_issuer(const TcGcnArgs &a, uint64_t *full, uint64_t *empty, uint64_t *tfull, uint64_t *tempty,
+                                               const uint32_t smem_base, const uint32_t tmem_base, const int cta, const int ncta) {
+  const int n_pass = a.cout / 64;
+  const int nkb = a.cin / kBK;
+  PipeState ps;
+  bool ok = true;
+  int it = 0;
+  const bool mtr = TRACE && a.trace != nullptr && cta == 0;
+  unsigned long long mt[2] = {0, 0};
+  const long long mstart = mtr ? clock64() : 0;
+  for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+    for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
+      const int acc = it & 1;
+      const long long m0 = mtr ? clock64() : 0;
+      ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
+      if (!ok) break;
+      if (mtr) mt[0] += clock64() - m0;
+      ptx::tc_fence_after();
+      const uint32_t d = tmem_base + acc * Cfg::kAccStride;
+      for (int kc = 0; kc < nkb; ++kc) {
+        const long long m1 = mtr ? clock64() : 0;
+        ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(pass * 16 + kc));
+        if (!ok) break;
+        if (mtr) mt[1] += clock64() - m1;
+        ptx::tc_fence_after();
+        const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
+        issue_kblock<Cfg::kN>(d, st, st + kABytes, st + 2 * kABytes, st + 2 * kABytes + Cfg::kBBytes, kc == 0);
+        ptx::umma_commit(&empty[ps.stage]);
+        ps.advance<Cfg::kStages>();
+      }
+      if (ok) ptx::umma_commit(&tfull[acc]);
+    }
+  }
+  if (mtr) {
+    a.trace[16] = mt[0];
+    a.trace[17] = mt[1];
+    a.trace[18] = clock64() - mstart;
   }
 }
 
@@ -745,80 +836,9 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
   constexpr int kChunks = 64 / kGcnChunk;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      bool ok = true;
-      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
-        const int row = a.x_row + tile * a.tile_tokens;
-        if (a.wait_cnt != nullptr) {
-          // the input rows of this tile come from the temporal-conv role of the same launch
-          const long long t0 = clock64();
-          while (ptx::ld_acquire_u32(a.wait_cnt + tile) < a.wait_need) {
-            if (*(volatile unsigned int *)a.dbg != 0 || clock64() - t0 > ptx::kWaitLimitCycles) {
-              atomicCAS(a.dbg, 0u, kDbgTileFlag | (unsigned)(tile & 0xffffff));
-              ok = false;
-              break;
-            }
-            __nanosleep(200);
-          }
-          if (!ok) break;
-          ptx::fence_proxy_async_all();  // order the acquire (generic proxy) before the TMA reads (async proxy)
-        }
-        for (int pass = 0; ok && pass < n_pass; ++pass) {
-          for (int kc = 0; kc < nkb; ++kc) {
-            ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(pass * 16 + kc));
-            if (!ok) break;
-            const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
-            ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
-            // the input tile is re-read once per pass (L2 hits): keep it until the last pass, then let it go
-            const uint64_t xpol = pass + 1 < n_pass ? ptx::kEvictNormal : ptx::kEvictFirst;
-            ptx::tma_load_2d_hint(st, &a.tm_x, &full[ps.stage], kc * kBK, row, xpol);
-            ptx::tma_load_2d_hint(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc, xpol);
-            ptx::tma_load_2d_hint(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, pass * Cfg::kN, ptx::kEvictLast);
-            ptx::tma_load_2d_hint(st + 2 * kABytes + Cfg::kBBytes, &a.tm_w, &full[ps.stage], kc * kBK, P * a.cout + pass * Cfg::kN,
-                                  ptx::kEvictLast);
-            ps.advance<Cfg::kStages>();
-          }
-        }
-      }
-    }
+    if (lane == 0) gcn_producer<Cfg, P>(a, full, empty, smem_base, cta, ncta);
   } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState ps;
-      bool ok = true;
-      int it = 0;
-      const bool mtr = TRACE && a.trace != nullptr && cta == 0;
-      unsigned long long mt[2] = {0, 0};
-      const long long mstart = mtr ? clock64() : 0;
-      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
-        for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
-          const int acc = it & 1;
-          const long long m0 = mtr ? clock64() : 0;
-          ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
-          if (!ok) break;
-          if (mtr) mt[0] += clock64() - m0;
-          ptx::tc_fence_after();
-          const uint32_t d = tmem_base + acc * Cfg::kAccStride;
-          for (int kc = 0; kc < nkb; ++kc) {
-            const long long m1 = mtr ? clock64() : 0;
-            ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(pass * 16 + kc));
-            if (!ok) break;
-            if (mtr) mt[1] += clock64() - m1;
-            ptx::tc_fence_after();
-            const uint32_t st = smem_base + ps.stage * Cfg::kStageBytes;
-            issue_kblock<Cfg::kN>(d, st, st + kABytes, st + 2 * kABytes, st + 2 * kABytes + Cfg::kBBytes, kc == 0);
-            ptx::umma_commit(&empty[ps.stage]);
-            ps.advance<Cfg::kStages>();
-          }
-          if (ok) ptx::umma_commit(&tfull[acc]);
-        }
-      }
-      if (mtr) {
-        a.trace[16] = mt[0];
-        a.trace[17] = mt[1];
-        a.trace[18] = clock64() - mstart;
-      }
-    }
+    if (lane == 0) gcn_mma_issuer<Cfg, TRACE>(a, full, empty, tfull, tempty, smem_base, tmem_base, cta, ncta);
   } else if (warp >= 4 && warp < 8) {
     // ---- drain: TMEM -> own-row terms folded -> exchange planes --------------------------------
     const int q = warp & 3;
@@ -1016,6 +1036,218 @@ template <int P, int STAGES, bool TRACE>
 __global__ void __launch_bounds__(512, 1) k_tc_gcn(const __grid_constant__ TcGcnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   gcn_body<P, STAGES, TRACE>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// =============================================================================================
+// Adaptive graph conv, GEMM + dense mix (AdaptiveGraphConvolution, models/a_gcn/a_gcn.py:52-69 with T = 1):
+//
+//   z[w] = sum_i sum_v M_i[v,w] * (W_i x[v]) + bias + gcn_residual(x)[w] ,   M_i = softmax_i + A_i + graph_attn_i
+//
+// Same TMA -> tcgen05 mainloop as k_tc_gcn (Y = X [W_0|W_1|W_2(|W_r)]^T, 64 output channels per pass), but the
+// mixing matrix is dense and differs per skeleton, so the epilogue changes:
+//   drain warps (4, thread = token row): copy 16-channel chunks of every part from TMEM to shared-memory planes
+//       (80-byte rows: conflict-free 16-byte stores, and sources are immediate offsets from a lane's skeleton);
+//   mix warps (8, lane = token row x 8-channel half): the 3*V coefficients of the lane's row sit in registers for
+//       the whole tile (loaded from the scratch k_tc_attn / k_agcn_attn wrote), every source row is a broadcast
+//       shared-memory read, 8 FMAs per 2 loads: the phase is bound by the FP32 pipe.
+// P = 4: part 3 = folded gcn_residual conv (added from its plane); P = 3: identity residual added from the input rows.
+// =============================================================================================
+template <int P, int STAGES>
+struct TcAgcnCfg {
+  static constexpr int kN = P * 64;
+  static constexpr int kBBytes = kN * kBK * 2;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kStages = STAGES;
+  static constexpr int kRowBytes = kGcnChunk * 4 + 16;           // 64-byte rows padded to 80
+  static constexpr int kPlaneBytes = kTileRows * kRowBytes;      // 10 KB
+  static constexpr int kExchBytes = P * kPlaneBytes;             // planes Y0, Y1, Y2 (, Y3)
+  static constexpr int kExchBufs = 2;
+  static constexpr int kExchOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kExchOff + kExchBufs * kExchBytes;
+  static constexpr int kBiasOff = kBarOff + 256;
+  static constexpr int kSmemBytes = kBiasOff + 256 * 4 + 1024;
+  static constexpr int kAccStride = 256;
+  static constexpr int kTmemCols = 512;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+};
+
+template <int P, int STAGES, int V>
+__device__ __forceinline__ void agcn_body(const TcGcnArgs &a, uint8_t *smem_raw, const int cta, const int ncta) {
+  using Cfg = TcAgcnCfg<P, STAGES>;
+  constexpr int VP = (V + 3) / 4 * 4;  // == dense_vp
+  uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *empty = full + Cfg::kStages;
+  uint64_t *tfull = empty + Cfg::kStages;
+  uint64_t *tempty = tfull + 2;
+  uint64_t *xfull = tempty + 2;
+  uint64_t *xempty = xfull + Cfg::kExchBufs;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xempty + Cfg::kExchBufs);
+  float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 4);
+    }
+    for (int s = 0; s < Cfg::kExchBufs; ++s) {
+      ptx::mbar_init(&xfull[s], 4);
+      ptx::mbar_init(&xempty[s], 8);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tm_x);
+    ptx::prefetch_tmap(&a.tm_w);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < a.cout; i += blockDim.x) bias_s[i] = a.epi.bias[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int n_pass = a.cout / 64;
+  constexpr int kChunks = 64 / kGcnChunk;
+
+  if (warp == 0) {
+    if (lane == 0) gcn_producer<Cfg, P>(a, full, empty, smem_base, cta, ncta);
+  } else if (warp == 1) {
+    if (lane == 0) gcn_mma_issuer<Cfg, false>(a, full, empty, tfull, tempty, smem_base, tmem_base, cta, ncta);
+  } else if (warp >= 4 && warp < 8) {
+    // ---- drain: TMEM -> exchange planes, no arithmetic -----------------------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    bool ok = true;
+    int it = 0;
+    uint32_t xc = 0;
+    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+      for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
+        const int acc = it & 1;
+        ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+        if (!ok) break;
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccStride;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++xc) {
+          uint32_t y[P][16];
+#pragma unroll
+          for (int part = 0; part < P; ++part) ptx::tmem_ld_32x16(taddr + part * 64 + c * kGcnChunk, y[part]);
+          ptx::tmem_ld_wait();
+          const uint32_t b = xc % Cfg::kExchBufs;
+          const uint32_t use = xc / Cfg::kExchBufs;
+          ok = ptx::mbar_wait(&xempty[b], (use & 1) ^ 1, a.dbg, kDbgEpiExchEmpty | (xc & 0xffff));
+          if (!ok) break;
+          uint8_t *buf = smem + Cfg::kExchOff + b * Cfg::kExchBytes + row * Cfg::kRowBytes;
+#pragma unroll
+          for (int part = 0; part < P; ++part)
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<uint4 *>(buf + part * Cfg::kPlaneBytes + ch * 16) =
+                  make_uint4(y[part][4 * ch], y[part][4 * ch + 1], y[part][4 * ch + 2], y[part][4 * ch + 3]);
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&xfull[b]);
+        }
+        if (!ok) break;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- dense mix ---------------------------------------------------------------------------------
+    const int m = warp - 8;
+    const int row = m * 16 + (lane >> 1), half = lane & 1;
+    const bool row_ok = row < a.tile_tokens;
+    const int sk0 = row_ok ? row - row % V : 0;  // first row of the lane's skeleton
+    const uint32_t src_off = (uint32_t)(sk0 * Cfg::kRowBytes + half * 32);  // source vertex v adds v * kRowBytes
+    const uint32_t own_off = (uint32_t)(row * Cfg::kRowBytes + half * 32);
+    bool ok = true;
+    uint32_t xc = 0;
+    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+      const long long tok = (long long)tile * a.tile_tokens + row;
+      const bool valid = row_ok && tok < a.n_tokens;
+      // mixing row of this token: 3 partitions x V sources, in registers for the whole tile
+      float4 cf[3][VP / 4];
+#pragma unroll
+      for (int part = 0; part < 3; ++part)
+#pragma unroll
+        for (int j = 0; j < VP / 4; ++j)
+          cf[part][j] = valid ? *reinterpret_cast<const float4 *>(a.dense + tok * a.dense_ld + part * VP + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pass = 0; ok && pass < n_pass; ++pass) {
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++xc) {
+          const int c0 = pass * 64 + c * kGcnChunk + half * 8;
+          float z[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = bias_s[c0 + j];
+          if (P == 3 && valid) {  // identity gcn_residual: the token's own input row (hi + lo)
+            const uint4 h = ptx::ldg_v4(reinterpret_cast<const uint4 *>(a.epi.r_hi + tok * a.epi.cs_r + c0));
+            const uint4 l = ptx::ldg_v4(reinterpret_cast<const uint4 *>(a.epi.r_lo + tok * a.epi.cs_r + c0));
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              z[2 * w] += bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]);
+              z[2 * w + 1] += bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]);
+            }
+          }
+          const uint32_t b = xc % Cfg::kExchBufs;
+          const uint32_t use = xc / Cfg::kExchBufs;
+          ok = ptx::mbar_wait(&xfull[b], use & 1, a.dbg, kDbgEpiExchFull | (xc & 0xffff));
+          if (!ok) break;
+          const uint8_t *buf = smem + Cfg::kExchOff + b * Cfg::kExchBytes;
+          if (P == 4) {
+            const float4 r0 = *reinterpret_cast<const float4 *>(buf + 3 * Cfg::kPlaneBytes + own_off);
+            const float4 r1 = *reinterpret_cast<const float4 *>(buf + 3 * Cfg::kPlaneBytes + own_off + 16);
+            z[0] += r0.x; z[1] += r0.y; z[2] += r0.z; z[3] += r0.w;
+            z[4] += r1.x; z[5] += r1.y; z[6] += r1.z; z[7] += r1.w;
+          }
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            const uint8_t *pl = buf + part * Cfg::kPlaneBytes + src_off;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              const float4 q4 = cf[part][v >> 2];
+              const float coef = (v & 3) == 0 ? q4.x : (v & 3) == 1 ? q4.y : (v & 3) == 2 ? q4.z : q4.w;
+              const float4 y0 = *reinterpret_cast<const float4 *>(pl + v * Cfg::kRowBytes);
+              const float4 y1 = *reinterpret_cast<const float4 *>(pl + v * Cfg::kRowBytes + 16);
+              z[0] = fmaf(coef, y0.x, z[0]); z[1] = fmaf(coef, y0.y, z[1]); z[2] = fmaf(coef, y0.z, z[2]); z[3] = fmaf(coef, y0.w, z[3]);
+              z[4] = fmaf(coef, y1.x, z[4]); z[5] = fmaf(coef, y1.y, z[5]); z[6] = fmaf(coef, y1.z, z[6]); z[7] = fmaf(coef, y1.w, z[7]);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&xempty[b]);
+          if (valid) {
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float x0 = fmaxf(z[2 * w], 0.f), x1 = fmaxf(z[2 * w + 1], 0.f);
+              oh[w] = pack_bf16x2(x0, x1);
+              ol[w] = pack_bf16x2(x0 - bf16_lo_as_float(oh[w]), x1 - bf16_hi_as_float(oh[w]));
+            }
+            *reinterpret_cast<uint4 *>(a.epi.y_hi + tok * a.epi.cs_out + c0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            *reinterpret_cast<uint4 *>(a.epi.y_lo + tok * a.epi.cs_out + c0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int P, int STAGES, int V>
+__global__ void __launch_bounds__(512, 1) k_tc_agcn(const __grid_constant__ TcGcnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  agcn_body<P, STAGES, V>(a, smem_raw, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // =============================================================================================
