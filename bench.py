@@ -224,7 +224,7 @@ def run_ours(args, rank, world, local_rank):
         t += 1
     barrier()
     prof = {}
-    for kind, name in ((0, "input"), (1, "gcn"), (2, "tcn"), (3, "head")):
+    for kind, name in ((0, "input"), (1, "gcn"), (2, "tcn"), (3, "head"), (4, "attn")):
         ms, n = model.profile_read(kind)
         prof[name] = {"ms": ms, "launches": n}
     per_block = []
@@ -232,6 +232,8 @@ def run_ours(args, rank, world, local_rank):
         g_ms, g_n = model.profile_read(1, b)
         t_ms, t_n = model.profile_read(2, b)
         per_block.append({"gcn_ms": g_ms, "gcn_n": g_n, "tcn_ms": t_ms, "tcn_n": t_n})
+        if args.workload == "coa_gcn":
+            per_block[-1]["attn_ms"], per_block[-1]["attn_n"] = model.profile_read(4, b)
     model.profile(False)
     if world > 1:
         tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -306,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
     k_tf_credit = 2.0 * k_macs / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
     issued_k = (9 * cout + res_k) if kname == "tcn" else 4 * cin
     k_tf_issued = 3 * 2.0 * (tokens * 128.0 / 125.0) * cout * issued_k / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 else None
+    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 and not (args.workload == "coa_gcn" and kname == "gcn") else None
     step_bytes = algo["state"] + algo["io"]
     line = {
         "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

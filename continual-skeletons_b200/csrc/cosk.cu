@@ -52,9 +52,10 @@ struct BlockW {
   int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
   bool mix_diag0 = true;  // partition 0 has only self links
   // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
-  __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr;
-  CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half;  // _half: box of cout/2 rows for the CTA-pair kernel
+  __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr, *d_att_w16 = nullptr;
+  CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half, map_att_w;  // _half: box of cout/2 rows for the CTA-pair kernel
   bool tc_gcn = false, tc_tcn = false;
+  bool tc_attn = false;  // adaptive graph conv: attention half on the tcgen05 kernel
   bool tcn_res_kblock = false;  // tensor-core temporal conv: the residual enters as extra K-blocks of the GEMM (folded
                                 // strided conv, or identity weights for the narrow layers) instead of epilogue loads
   long long n_in = 0, n_out = 0;
@@ -81,6 +82,7 @@ struct cosk_model {
   int merge_min_tiles = 4 * 148;  // below this the two CTA groups are not worth splitting (COSK_MERGE_MIN_TILES)
   int merge_split64 = 100;  // CTAs given to the temporal-conv role (64-channel layers)
   int merge_split128 = 92;  // same for the 128-channel layers (CTA pairs)
+  int attn_tc = 1;  // attention half of the adaptive graph conv on tcgen05 (COSK_ATTN_TC=0: fp32 CUDA-core kernel)
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
   int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
@@ -338,6 +340,22 @@ int prepare(cosk_model *m) {
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
       if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
     }
+    b.tc_attn = adaptive && b.tc_gcn && m->attn_tc && tc_width(bc.cout);
+    if (b.tc_attn) {
+      // per partition: hi rows of (theta, phi), then their lo rows -- one stacked operand of 4*IC rows
+      const int ic = bc.cout / 4;
+      std::vector<uint16_t> st((size_t)12 * ic * bc.cin);
+      for (int part = 0; part < 3; ++part)
+        for (int r = 0; r < 2 * ic; ++r)
+          for (int k = 0; k < bc.cin; ++k) {
+            const float w = b.att_w[((size_t)part * 2 * ic + r) * bc.cin + k];
+            const uint16_t h = f2bf(w);
+            st[((size_t)part * 4 * ic + r) * bc.cin + k] = h;
+            st[((size_t)part * 4 * ic + 2 * ic + r) * bc.cin + k] = f2bf(w - bf2f(h));
+          }
+      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_att_w16), st.data(), st.size()))) return rc;
+      if ((rc = make_map(m, &b.map_att_w, b.d_att_w16, (uint64_t)bc.cin, (uint64_t)12 * ic, (uint32_t)(4 * ic)))) return rc;
+    }
     if (b.tc_tcn) {
       // The delayed residual x_{n-4} is streamed through the operand ring like a tenth tap: with the folded
       // strided 1x1 conv as its weights (layers 5 and 8), or -- for the identity residual of the HBM-bound
@@ -446,8 +464,21 @@ int launch_tc_agcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
   return COSK_OK;
 }
 
+template <int IC, int V>
+int launch_tc_attn(cosk_model *m, const TcAttnArgs &args, cudaStream_t s) {
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  CK(launch_k(m, k_tc_attn<IC, V>, dim3(grid), dim3(256), TcAttnCfg<IC, V>::kSmemBytes, s, args));
+  return COSK_OK;
+}
+
 int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_agcn_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMaxSmem));
+  CK(cudaFuncSetAttribute(k_tc_attn<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<16, 25>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_attn<32, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<32, 25>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_attn<64, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<64, 25>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_attn<16, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<16, 18>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_attn<32, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<32, 18>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_attn<64, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<64, 18>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcn<4, 1, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<4, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcn<3, 2, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<3, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcn<4, 1, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcnCfg<4, 1>::kSmemBytes));
@@ -591,10 +622,33 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
   const cosk_block_cfg &bc = m->cfg.blocks[i];
   BlockW &b = m->blk[i];
   const int res_conv = bc.cin != bc.cout ? 1 : 0;
-  int rc = prof_mark(m, 1, i, s);
-  if (rc) return rc;
   const bool adaptive = m->cfg.graph_conv == COSK_GCONV_ADAPTIVE;
-  if (adaptive) {
+  int rc = prof_mark(m, adaptive ? 4 : 1, i, s);
+  if (rc) return rc;
+  if (adaptive && b.tc_attn) {
+    TcAttnArgs t;
+    t.tm_x = in.map;
+    t.tm_w = b.map_att_w;
+    t.x_row = (int)in.row_hi(in_slot);
+    t.t_alloc = (int)m->t_alloc;
+    t.cin = bc.cin;
+    t.n_tiles = m->n_tiles;
+    t.tile_tokens = m->tile_tokens;
+    t.n_tokens = m->n_tokens;
+    t.bias = b.d_att_b;
+    t.adj = b.d_adj;
+    t.dense = m->d_dense;
+    t.dense_ld = 3 * m->dense_vp;
+    t.dbg = m->d_dbg;
+    const int ic = bc.cout / 4;
+    if (m->cfg.vertices == 25)
+      rc = ic == 16 ? launch_tc_attn<16, 25>(m, t, s) : ic == 32 ? launch_tc_attn<32, 25>(m, t, s) : launch_tc_attn<64, 25>(m, t, s);
+    else
+      rc = ic == 16 ? launch_tc_attn<16, 18>(m, t, s) : ic == 32 ? launch_tc_attn<32, 18>(m, t, s) : launch_tc_attn<64, 18>(m, t, s);
+    if (rc) return rc;
+    m->launches++;
+    if ((rc = prof_mark(m, 1, i, s))) return rc;
+  } else if (adaptive) {
     // attention half: the per-token mixing rows of this frame go to the dense scratch
     AttnArgs t;
     t.x_hi = in.hi(in_slot);
@@ -613,6 +667,7 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     t.dense_vp = m->dense_vp;
     CK(launch_k(m, k_agcn_attn, dim3(m->n_tiles), dim3(256), (size_t)2 * t.inter_c * kTileRows * sizeof(float), s, t));
     m->launches++;
+    if ((rc = prof_mark(m, 1, i, s))) return rc;
   }
   if (b.tc_gcn && adaptive) {
     TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
@@ -855,6 +910,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
+  if (const char *e = getenv("COSK_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char *e = getenv("COSK_TCN_IDENTITY_MMA")) m->tcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_MERGE")) m->merge = atoi(e);
   if (const char *e = getenv("COSK_MERGE_MIN_TILES")) m->merge_min_tiles = atoi(e);
@@ -913,6 +969,7 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_adj);
     dfree(b.d_gcn_w16);
     dfree(b.d_tcn_w16);
+    dfree(b.d_att_w16);
   }
   dfree(m->d_bn_scale);
   dfree(m->d_bn_shift);

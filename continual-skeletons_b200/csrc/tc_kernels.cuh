@@ -1251,6 +1251,227 @@ __global__ void __launch_bounds__(512, 1) k_tc_agcn(const __grid_constant__ TcGc
 }
 
 // =============================================================================================
+// Adaptive graph conv, attention half on tcgen05 (AdaptiveGraphConvolution.forward with T = 1,
+// models/a_gcn/a_gcn.py:52-63).  Work item = (token tile, partition i):
+//   mainloop   [theta_i | phi_i] = X [128 x cin] * [Wa_i | Wb_i]^T, 2*IC columns, stacked-B split products
+//              (the hi and lo weight rows of a partition are adjacent in memory: one operand of 4*IC rows);
+//   epilogue   (4 warps, thread = token row) accumulator -> shared memory (theta in a skeleton-padded
+//              layout so a lane reads its skeleton's V values with 16-byte broadcast loads), then per row w:
+//              S[v] = <theta[v], phi[w]> / IC, softmax over v, + (A + graph_attn)_i[v][w], written as the
+//              token's mixing row to the dense scratch k_tc_agcn reads.
+// The next item's MMAs run while the epilogue warps work (two accumulators in TMEM).
+// =============================================================================================
+struct TcAttnArgs {
+  CUtensorMap tm_x;  // block input ring, box {64, 128}
+  CUtensorMap tm_w;  // [3 partitions][hi: theta, phi | lo: theta, phi][cin], box {64, 4*IC}
+  int x_row, t_alloc, cin;
+  int n_tiles, tile_tokens;
+  long long n_tokens;
+  const float *bias;  // [3][2*IC]
+  const float *adj;   // [3][V][V]
+  float *dense;
+  int dense_ld;
+  unsigned int *dbg;
+};
+
+template <int IC, int V>
+struct TcAttnCfg {
+  static constexpr int kSkp = (V + 3) / 4 * 4;                 // skeleton pitch in the theta buffer == dense_vp
+  static constexpr int kSkel = kTileRows / V;                  // skeletons per tile
+  static constexpr int kThetaPitch = kSkel * kSkp;             // floats per channel row
+  static constexpr int kBBytes = 4 * IC * kBK * 2;             // stacked hi + lo rows
+  static constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  static constexpr int kStages = 2;
+  static constexpr int kThetaOff = kStages * (2 * kABytes + 4 * 64 * kBK * 2);  // stages sized for IC = 64: 1024-byte aligned
+  static constexpr int kStageStride = 2 * kABytes + 4 * 64 * kBK * 2;
+  static constexpr int kPhiOff = kThetaOff + IC * kThetaPitch * 4;
+  static constexpr int kAdjOff = kPhiOff + IC * kTileRows * 4;
+  static constexpr int kBiasOff = kAdjOff + (3 * V * V * 4 + 15) / 16 * 16;
+  static constexpr int kBarOff = kBiasOff + 6 * IC * 4;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kAccCols = 4 * IC;                      // hi-product half | lo-weight half
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+  static_assert(IC % 16 == 0 && IC <= 64, "embedding width");
+};
+
+template <int IC, int V>
+__global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAttnArgs a) {
+  using Cfg = TcAttnCfg<IC, V>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float *theta_s = reinterpret_cast<float *>(smem + Cfg::kThetaOff);  // [IC][kThetaPitch]
+  float *phi_s = reinterpret_cast<float *>(smem + Cfg::kPhiOff);      // [IC][128]
+  float *adj_s = reinterpret_cast<float *>(smem + Cfg::kAdjOff);      // [3][V][V]
+  float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);    // [3][2*IC]
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *empty = full + Cfg::kStages;
+  uint64_t *tfull = empty + Cfg::kStages;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tm_x);
+    ptx::prefetch_tmap(&a.tm_w);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) adj_s[i] = a.adj[i];
+  for (int i = threadIdx.x; i < 6 * IC; i += blockDim.x) bias_s[i] = a.bias[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int nkb = a.cin / kBK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+        const int row = a.x_row + tile * a.tile_tokens;
+        for (int part = 0; ok && part < 3; ++part) {
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(part * 16 + kc));
+            if (!ok) break;
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageStride;
+            ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
+            ptx::tma_load_2d_hint(st, &a.tm_x, &full[ps.stage], kc * kBK, row, ptx::kEvictNormal);
+            ptx::tma_load_2d_hint(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc, ptx::kEvictNormal);
+            ptx::tma_load_2d_hint(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, part * 4 * IC, ptx::kEvictLast);
+            ps.advance<Cfg::kStages>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      int it = 0;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+        for (int part = 0; ok && part < 3; ++part, ++it) {
+          const int acc = it & 1;
+          ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
+          if (!ok) break;
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + acc * Cfg::kAccCols;
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(part * 16 + kc));
+            if (!ok) break;
+            ptx::tc_fence_after();
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageStride;
+            issue_kblock_stacked<4 * IC>(d, st, st + kABytes, st + 2 * kABytes, kc == 0);
+            ptx::umma_commit(&empty[ps.stage]);
+            ps.advance<Cfg::kStages>();
+          }
+          if (ok) ptx::umma_commit(&tfull[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool row_ok = row < a.tile_tokens;
+    const int sk = row_ok ? row / V : 0, wv = row_ok ? row - sk * V : 0;
+    const int th_col = sk * Cfg::kSkp;  // this row's skeleton in the theta buffer
+    bool ok = true;
+    int it = 0;
+    for (int tile = cta; tile < a.n_tiles; tile += ncta) {
+      const long long tok = (long long)tile * a.tile_tokens + row;
+      const bool valid = row_ok && tok < a.n_tokens;
+      for (int part = 0; part < 3; ++part, ++it) {
+        const int acc = it & 1;
+        // a warp whose wait expired keeps walking the items (named barriers below), it only stops computing
+        if (ok) ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+        if (ok) {
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 2 * IC; c0 += 16) {
+            uint32_t yh[16], yl[16];
+            ptx::tmem_ld_32x16(taddr + c0, yh);
+            ptx::tmem_ld_32x16(taddr + 2 * IC + c0, yl);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+              const float *bb = bias_s + part * 2 * IC + c0;
+              if (c0 < IC) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  theta_s[(c0 + j) * Cfg::kThetaPitch + th_col + wv] = __uint_as_float(yh[j]) + __uint_as_float(yl[j]) + bb[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  phi_s[(c0 - IC + j) * kTileRows + row] = __uint_as_float(yh[j]) + __uint_as_float(yl[j]) + bb[j];
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);  // accumulator drained: the next item's MMAs may start
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // theta / phi of the whole tile are in shared memory
+        if (ok && valid) {
+          float sv[Cfg::kSkp];
+#pragma unroll
+          for (int v = 0; v < Cfg::kSkp; ++v) sv[v] = 0.f;
+#pragma unroll 2
+          for (int c = 0; c < IC; ++c) {
+            const float ph = phi_s[c * kTileRows + row];
+            const float4 *th = reinterpret_cast<const float4 *>(theta_s + c * Cfg::kThetaPitch + th_col);
+#pragma unroll
+            for (int j = 0; j < Cfg::kSkp / 4; ++j) {
+              const float4 t = th[j];
+              sv[4 * j] = fmaf(t.x, ph, sv[4 * j]);
+              sv[4 * j + 1] = fmaf(t.y, ph, sv[4 * j + 1]);
+              sv[4 * j + 2] = fmaf(t.z, ph, sv[4 * j + 2]);
+              sv[4 * j + 3] = fmaf(t.w, ph, sv[4 * j + 3]);
+            }
+          }
+          float mx = -INFINITY;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            sv[v] = sv[v] / (float)IC;
+            mx = fmaxf(mx, sv[v]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            sv[v] = expf(sv[v] - mx);
+            sum += sv[v];
+          }
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int v = 0; v < Cfg::kSkp; ++v) sv[v] = v < V ? fmaf(sv[v], inv, adj_s[(part * V + v) * V + wv]) : 0.f;
+          float4 *dst = reinterpret_cast<float4 *>(a.dense + tok * a.dense_ld + part * Cfg::kSkp);
+#pragma unroll
+          for (int j = 0; j < Cfg::kSkp / 4; ++j) dst[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // buffers free for the next item
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =============================================================================================
 // One launch, two roles: CTAs [0, n_tcn) run the temporal conv of block L, the remaining CTAs the graph
 // conv of block L+1, which consumes the temporal conv's output tile by tile (per-tile release/acquire
 // counters in global memory).  The temporal convs of the 64- and 128-channel layers are bound by HBM and

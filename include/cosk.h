@@ -136,7 +136,7 @@ int64_t cosk_launch_count(const cosk_model *m);
 int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block);
 
 /* Per-kernel-kind device timing with CUDA events on the launching stream.
- * kinds: 0 input, 1 gcn, 2 tcn, 3 pool+fc; enable before the timed region, then read. */
+ * kinds: 0 input, 1 gcn, 2 tcn, 3 pool+fc, 4 attention half of the adaptive gcn; enable before the timed region, then read. */
 int cosk_profile_enable(cosk_model *m, int32_t on);
 /* Sums the event-measured device time (ms) and launch count of (kind, block) since enable;
  * block < 0 sums over blocks.  Synchronises the recorded events. */
