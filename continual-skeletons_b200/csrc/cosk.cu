@@ -648,6 +648,24 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     if (rc) return rc;
     m->launches++;
     if ((rc = prof_mark(m, 1, i, s))) return rc;
+  } else if (adaptive && m->cfg.path == COSK_PATH_AUTO && bc.cin <= 8 && bc.cout == 64 && (m->cfg.vertices == 25 || m->cfg.vertices == 18)) {
+    // narrow first layer: embeddings computed per thread, same per-row softmax as the tensor-core kernel
+    AttnSmallArgs t;
+    t.x_hi = in.hi(in_slot);
+    t.x_lo = in.lo(in_slot);
+    t.cs_in = in.cs;
+    t.cin = bc.cin;
+    t.w = b.d_att_w;
+    t.bias = b.d_att_b;
+    t.adj = b.d_adj;
+    t.n_tokens = m->n_tokens;
+    t.tile_tokens = m->tile_tokens;
+    t.dense = m->d_dense;
+    t.dense_ld = 3 * m->dense_vp;
+    if (m->cfg.vertices == 25) CK(launch_k(m, k_attn_small<16, 25>, dim3(m->n_tiles), dim3(128), 0, s, t));
+    else CK(launch_k(m, k_attn_small<16, 18>, dim3(m->n_tiles), dim3(128), 0, s, t));
+    m->launches++;
+    if ((rc = prof_mark(m, 1, i, s))) return rc;
   } else if (adaptive) {
     // attention half: the per-token mixing rows of this frame go to the dense scratch
     AttnArgs t;

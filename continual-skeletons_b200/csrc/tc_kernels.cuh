@@ -1295,6 +1295,50 @@ struct TcAttnCfg {
   static_assert(IC % 16 == 0 && IC <= 64, "embedding width");
 };
 
+// One token row w of the attention (thread = row): S[v] = <theta[v], phi[w]> / IC over the V vertices of the row's
+// skeleton, softmax over v, plus the static term; written as the row's mixing coefficients of partition `part`.
+// theta_s: [IC][kThetaPitch] skeleton-padded, phi_s: [IC][128], adj_s: [3][V][V].
+template <int IC, int V>
+__device__ __forceinline__ void attn_softmax_row(const float *theta_s, const float *phi_s, const float *adj_s, int part, int row,
+                                                 int th_col, int wv, float *dense_row) {
+  constexpr int kSkp = (V + 3) / 4 * 4;
+  constexpr int kThetaPitch = (kTileRows / V) * kSkp;
+  float sv[kSkp];
+#pragma unroll
+  for (int v = 0; v < kSkp; ++v) sv[v] = 0.f;
+#pragma unroll 2
+  for (int c = 0; c < IC; ++c) {
+    const float ph = phi_s[c * kTileRows + row];
+    const float4 *th = reinterpret_cast<const float4 *>(theta_s + c * kThetaPitch + th_col);
+#pragma unroll
+    for (int j = 0; j < kSkp / 4; ++j) {
+      const float4 t = th[j];
+      sv[4 * j] = fmaf(t.x, ph, sv[4 * j]);
+      sv[4 * j + 1] = fmaf(t.y, ph, sv[4 * j + 1]);
+      sv[4 * j + 2] = fmaf(t.z, ph, sv[4 * j + 2]);
+      sv[4 * j + 3] = fmaf(t.w, ph, sv[4 * j + 3]);
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    sv[v] = sv[v] / (float)IC;
+    mx = fmaxf(mx, sv[v]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    sv[v] = expf(sv[v] - mx);
+    sum += sv[v];
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int v = 0; v < kSkp; ++v) sv[v] = v < V ? fmaf(sv[v], inv, adj_s[(part * V + v) * V + wv]) : 0.f;
+  float4 *dst = reinterpret_cast<float4 *>(dense_row + part * kSkp);
+#pragma unroll
+  for (int j = 0; j < kSkp / 4; ++j) dst[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
+}
+
 template <int IC, int V>
 __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAttnArgs a) {
   using Cfg = TcAttnCfg<IC, V>;
@@ -1426,42 +1470,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAt
           if (lane == 0) ptx::mbar_arrive(&tempty[acc]);  // accumulator drained: the next item's MMAs may start
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // theta / phi of the whole tile are in shared memory
-        if (ok && valid) {
-          float sv[Cfg::kSkp];
-#pragma unroll
-          for (int v = 0; v < Cfg::kSkp; ++v) sv[v] = 0.f;
-#pragma unroll 2
-          for (int c = 0; c < IC; ++c) {
-            const float ph = phi_s[c * kTileRows + row];
-            const float4 *th = reinterpret_cast<const float4 *>(theta_s + c * Cfg::kThetaPitch + th_col);
-#pragma unroll
-            for (int j = 0; j < Cfg::kSkp / 4; ++j) {
-              const float4 t = th[j];
-              sv[4 * j] = fmaf(t.x, ph, sv[4 * j]);
-              sv[4 * j + 1] = fmaf(t.y, ph, sv[4 * j + 1]);
-              sv[4 * j + 2] = fmaf(t.z, ph, sv[4 * j + 2]);
-              sv[4 * j + 3] = fmaf(t.w, ph, sv[4 * j + 3]);
-            }
-          }
-          float mx = -INFINITY;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            sv[v] = sv[v] / (float)IC;
-            mx = fmaxf(mx, sv[v]);
-          }
-          float sum = 0.f;
-#pragma unroll
-          for (int v = 0; v < V; ++v) {
-            sv[v] = expf(sv[v] - mx);
-            sum += sv[v];
-          }
-          const float inv = 1.0f / sum;
-#pragma unroll
-          for (int v = 0; v < Cfg::kSkp; ++v) sv[v] = v < V ? fmaf(sv[v], inv, adj_s[(part * V + v) * V + wv]) : 0.f;
-          float4 *dst = reinterpret_cast<float4 *>(a.dense + tok * a.dense_ld + part * Cfg::kSkp);
-#pragma unroll
-          for (int j = 0; j < Cfg::kSkp / 4; ++j) dst[j] = make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]);
-        }
+        if (ok && valid) attn_softmax_row<IC, V>(theta_s, phi_s, adj_s, part, row, th_col, wv, a.dense + tok * a.dense_ld);
         asm volatile("bar.sync 1, 128;" ::: "memory");  // buffers free for the next item
       }
     }
@@ -1469,6 +1478,61 @@ __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAt
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// Attention half for a narrow input (cin <= 8: the 3-channel first layer): the embeddings are a handful of
+// FMAs per token, so there is no GEMM to speak of -- each thread computes theta / phi of its token row straight
+// into the shared-memory buffers and the same per-row softmax follows.  One token tile per CTA, 128 threads.
+struct AttnSmallArgs {
+  const __nv_bfloat16 *x_hi, *x_lo;
+  int cs_in, cin;
+  const float *w;     // [cin][6*IC] k-major
+  const float *bias;  // [6*IC]
+  const float *adj;
+  long long n_tokens;
+  int tile_tokens;
+  float *dense;
+  int dense_ld;
+};
+
+template <int IC, int V>
+__global__ void __launch_bounds__(128) k_attn_small(AttnSmallArgs a) {
+  constexpr int kSkp = (V + 3) / 4 * 4;
+  constexpr int kThetaPitch = (kTileRows / V) * kSkp;
+  __shared__ __align__(16) float theta_s[IC * kThetaPitch];
+  __shared__ __align__(16) float phi_s[IC * kTileRows];
+  __shared__ float adj_s[3 * V * V];
+  __shared__ float w_s[8 * 6 * IC + 6 * IC];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 3 * V * V; i += blockDim.x) adj_s[i] = a.adj[i];
+  for (int i = threadIdx.x; i < a.cin * 6 * IC; i += blockDim.x) w_s[i] = a.w[i];
+  for (int i = threadIdx.x; i < 6 * IC; i += blockDim.x) w_s[8 * 6 * IC + i] = a.bias[i];
+  pdl_wait();
+  const int row = threadIdx.x;
+  const long long tok = (long long)blockIdx.x * a.tile_tokens + row;
+  const bool valid = row < a.tile_tokens && tok < a.n_tokens;
+  const int sk = row < a.tile_tokens ? row / V : 0, wv = row < a.tile_tokens ? row - sk * V : 0;
+  const int th_col = sk * kSkp;
+  float x[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) x[c] = (valid && c < a.cin) ? join_bf16(a.x_hi[tok * a.cs_in + c], a.x_lo[tok * a.cs_in + c]) : 0.f;
+  __syncthreads();
+  for (int part = 0; part < 3; ++part) {
+    if (row < a.tile_tokens) {
+#pragma unroll 4
+      for (int n = 0; n < 2 * IC; ++n) {
+        float v = w_s[8 * 6 * IC + part * 2 * IC + n];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.cin) v = fmaf(x[c], w_s[c * 6 * IC + part * 2 * IC + n], v);
+        if (n < IC) theta_s[n * kThetaPitch + th_col + wv] = v;
+        else phi_s[(n - IC) * kTileRows + row] = v;
+      }
+    }
+    __syncthreads();
+    if (valid) attn_softmax_row<IC, V>(theta_s, phi_s, adj_s, part, row, th_col, wv, a.dense + tok * a.dense_ld);
+    __syncthreads();
+  }
 }
 
 // =============================================================================================

@@ -373,3 +373,42 @@ def test_coa_gcn_schedule_and_blocks_vs_step_oracle():
                     e = _rel_err(m.read_block(i).cpu(), feats[i][:, :, n_out - 1])
                     assert e < 2e-4, (t, i, e)
     assert m.device_error() == 0
+
+
+def test_coa_gcn_many_streams_replicated_and_reset():
+    """Hundreds of CoA-GCN streams through the tiled attention / dense-mix kernels: replicas of a stream give
+    bit-identical logits, and a reset reproduces them exactly."""
+    arch, sd, m = _load_model(cs.CoAGcn, weights.coa_gcn_arch, True)
+    base = weights.make_input((2, 3, 300, 25, 2), seed=11).to(DEV)
+    small = m.forward_steps(base)
+    assert m.tensor_core_blocks() == [2] + [3] * 9
+    reps = 111  # 222 streams: not a multiple of the 2.5 streams per tile
+    big = m.forward_steps(base.repeat(reps, 1, 1, 1, 1))
+    assert m.device_error() == 0
+    assert tuple(big.shape) == (2 * reps, 60)
+    assert torch.equal(big.view(reps, 2, 60), small.unsqueeze(0).expand(reps, 2, 60))
+    m.clean_state()
+    assert torch.equal(m.forward_steps(base.repeat(reps, 1, 1, 1, 1)), big)
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+def test_adaptive_kinetics_skeleton_stack(path):
+    """Adaptive blocks on the 18-joint Kinetics graph (7 skeletons per 126-row tile) against the step oracle."""
+    blocks = [weights.BlockSpec(64, 64, 1, True), weights.BlockSpec(64, 128, 2, True)]
+    arch = ArchSpec(blocks, padding=4, skeleton="kinetics", head=False, block_names=["0.", "1."], graph_conv="adaptive")
+    sd = weights.make_state_dict(arch, seed=61, randomize=True)
+    x = weights.make_input((9, 64, 30, 18), seed=62)
+    stack = cs.CoStack([cs.BlockSpec(64, 64, 1, True), cs.BlockSpec(64, 128, 2, True)], padding=4, skeleton="kinetics",
+                       kernel_path=path, adaptive=True)
+    mapped = {}
+    for k, v in sd.items():
+        i, rest = k.split(".", 1)
+        mapped[f"{i}.0.0.{rest}" if rest.startswith("residual") else f"{i}.0.1.{rest}"] = v
+    stack.load_state_dict(mapped, strict=True)
+    want = step.StepModel(sd, arch).forward_steps(x)
+    got = stack.forward_steps(x.to(DEV))
+    assert stack.device_error() == 0
+    assert got is not None and tuple(got.shape) == tuple(want.shape)
+    assert _rel_err(got.cpu(), want) < BLOCK_RTOL, _rel_err(got.cpu(), want)
+    if path == "auto":
+        assert stack.tensor_core_blocks() == [3, 3]
