@@ -504,6 +504,14 @@ class CoModelBase(_CoBase):
         if pool_padding == -1:
             pool_padding = pool_size - math.ceil((T - self.receptive_field + self.padding + 1) / self.stride)
         self.pool_size, self.pool_padding = pool_size, max(0, pool_padding)
+        # The values above are those of the block stack, which is what the reference's pool formulas see
+        # (models/base.py:86-96 run before the full module list exists).  Once co.Sequential holds data_bn,
+        # blocks, pool and fc, its receptive_field / padding / delay include the pooling window -- and that is
+        # what warm_up (models/base.py:155) uses: 449 / 152 / 296 for CoST-GCN, 300 / 0 / 299 for CoST-GCN*.
+        self.stack_receptive_field, self.stack_padding = self.receptive_field, self.padding
+        self.receptive_field += (self.pool_size - 1) * self.stride
+        self.padding += self.pool_padding * self.stride
+        self.delay = self.receptive_field - 1 - self.padding
         self.call_mode = "forward_steps" if self.hparams.forward_mode == "frame" else "forward"
         if self.hparams.profile_model and self.hparams.forward_mode == "frame":
             self.input_shape = (c_in, self.stride, V, S)  # models/base.py:135-142
@@ -567,8 +575,7 @@ class CoModelBase(_CoBase):
     def forward(self, input):
         """models/base.py:166-181.  "frame": reset (unless profiling) and step through the clip.
         "clip": the reference runs the same weights as a regular padded network and keeps output 0;
-        that first output only depends on the first ``delay + stride * (pool_size - pool_padding - 1) + 1``
-        frames and no end padding, so it is produced here by stepping a fresh state."""
+        that first output only depends on the first ``delay + 1`` frames (297 / 300) and no end padding, so it is produced here by stepping a fresh state."""
         if self.hparams.forward_mode == "frame":
             if not self.hparams.profile_model:
                 self.clean_state()

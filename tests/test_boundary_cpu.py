@@ -72,12 +72,15 @@ def test_graph_bit_exact(golden):
 
 
 @pytest.mark.parametrize("cls,arch_fn,geom", [
-    (cs.CoStGcn, weights.cost_gcn_arch, (153, 4, 76, 76, 75, 19)),
-    (cs.CoStGcnMod, weights.cost_gcn_mod_arch, (81, 1, 0, 80, 220, 0)),
+    (cs.CoStGcn, weights.cost_gcn_arch, (449, 4, 152, 296, 75, 19)),
+    (cs.CoStGcnMod, weights.cost_gcn_mod_arch, (300, 1, 0, 299, 220, 0)),
 ])
 def test_geometry_and_key_mapping(cls, arch_fn, geom):
     m = cls(cls.configs().default_values())
     assert (m.receptive_field, m.stride, m.padding, m.delay, m.pool_size, m.pool_padding) == geom
+    arch = arch_fn()  # block stack alone: what the pool formulas of models/base.py:86-96 see
+    assert (m.stack_receptive_field, m.stack_padding) == (arch.receptive_field, arch.stack_padding)
+    assert m.delay == arch.receptive_field - 1 - arch.stack_padding + (arch.pool_size - 1 - arch.pool_padding) * arch.stack_stride
     assert m.input_shape == (3, 300, 25, 2) and m.output_shape == (60,)
     m.validate_attributes()
     own = list(m.state_dict().keys())

@@ -8,11 +8,14 @@ run pytest_gpu 1500 python -m pytest tests -m gpu -x -q
 run smoke 600 python __graft_entry__.py smoke
 run bench_auto 900 python bench.py --steps 200 --warmup 8
 run bench_auto_mod 900 python bench.py --workload cost_gcn_mod --steps 100 --warmup 8 --no-cpu-baseline
+run bench_coa 900 python bench.py --workload coa_gcn --steps 100 --warmup 8 --no-cpu-baseline
+run bench_script 600 python scripts/benchmark_all_ntu60.py
+run bench_reference 900 python bench.py --impl reference --steps 3 --warmup 1
 COSK_NCU=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file gpurun_out/launches.csv python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 echo "ncu_list rc=$?" >> gpurun_out/summary.txt
-COSK_NCU=1 timeout 900 ncu --profile-from-start off --set full --import-source on --clock-control none \
-   -k regex:"k_tc_gcn|k_gcn_small|k_head" -c 8 -o gpurun_out/prof_gcn python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gcn.log 2>&1
-echo "ncu_gcn rc=$?" >> gpurun_out/summary.txt
+COSK_NCU=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+   --log-file gpurun_out/launches_coa.csv python bench.py --workload coa_gcn --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_coa.log 2>&1
+echo "ncu_list_coa rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 for f in pytest_gpu smoke; do echo "== $f"; tail -12 gpurun_out/$f.log | cut -c1-400; done

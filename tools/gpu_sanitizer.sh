@@ -7,7 +7,7 @@ import sys, torch
 sys.path.insert(0, '.')
 import continual_skeletons_b200 as cs
 torch.manual_seed(0)
-for cls in (cs.CoStGcn, cs.CoStGcnMod):
+for cls in (cs.CoStGcn, cs.CoStGcnMod, cs.CoAGcn):
     m = cls({"dataset_name": "dummy_ntu"})
     x = torch.rand(7, 3, 30, 25, 2, device='cuda')   # 14 skeletons -> 3 tiles (odd: phantom tile in the pair kernels)
     for t in range(30):
@@ -19,6 +19,11 @@ x = torch.rand(9, 64, 25, 18, device='cuda')
 y = st.forward_steps(x)
 torch.cuda.synchronize()
 print('stack', None if y is None else tuple(y.shape), hex(st.device_error()))
+st = cs.CoStack([cs.BlockSpec(64, 128, 2, True), cs.BlockSpec(128, 128, 1, True)], padding=4, skeleton="kinetics", adaptive=True)
+x = torch.rand(9, 64, 25, 18, device='cuda')
+y = st.forward_steps(x)
+torch.cuda.synchronize()
+print('adaptive stack', None if y is None else tuple(y.shape), hex(st.device_error()), st.tensor_core_blocks())
 PY
 timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python /tmp/san.py > gpurun_out/sanitizer.log 2>&1
 echo "memcheck rc=$?"
