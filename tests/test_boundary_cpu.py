@@ -74,6 +74,7 @@ def test_graph_bit_exact(golden):
 @pytest.mark.parametrize("cls,arch_fn,geom", [
     (cs.CoStGcn, weights.cost_gcn_arch, (449, 4, 152, 296, 75, 19)),
     (cs.CoStGcnMod, weights.cost_gcn_mod_arch, (300, 1, 0, 299, 220, 0)),
+    (cs.CoAGcn, weights.coa_gcn_arch, (449, 4, 152, 296, 75, 19)),
 ])
 def test_geometry_and_key_mapping(cls, arch_fn, geom):
     m = cls(cls.configs().default_values())
@@ -213,3 +214,29 @@ def test_aggregate_preds_matches_numpy_reduction():
         cs.aggregate_preds([tp[0], tp[1][:3]])
     with pytest.raises(ValueError):
         cs.aggregate_preds(tp, "mean")
+
+
+def test_coa_gcn_host_model():
+    """CoAGcn: the reference's nested key names for the embedding convs (models/a_gcn/a_gcn.py:22-31 under the
+    CoSpatioTemporalBlock wrappers), its init (models/utils.py:10-19 with bs = 1; graph_attn = 1 as an additive term),
+    the folded tensors of the adaptive layout, and NTU-120 class count (BASELINE configs[2])."""
+    torch.manual_seed(0)
+    m = cs.CoAGcn({"dataset_name": "ntu120"})
+    assert m.num_classes == 120 and m._config().graph_conv == 1 and cs.CoStGcn()._config().graph_conv == 0
+    sd = m.state_dict()
+    assert sd["layers.layer1.gcn.a_conv.0.weight"].shape == (16, 3, 1, 1)
+    assert sd["layers.layer10.0.1.gcn.b_conv.2.weight"].shape == (64, 256, 1, 1)
+    assert torch.all(sd["layers.layer4.0.1.gcn.a_conv.1.bias"] == 0)
+    w = sd["layers.layer9.0.1.gcn.a_conv.0.weight"]
+    assert abs(float(w.std()) - (2.0 / 64) ** 0.5) < 2e-2  # kaiming fan_out over inter_c = 64 outputs
+    from continual_skeletons_b200 import model as _m
+
+    blk, spec = m.layers.layer5, m._specs[4]
+    t = _m._folded_block_tensors(blk, spec)
+    gcn = blk._cosk_parts[0]
+    assert torch.equal(t["mix"], (gcn.A + gcn.graph_attn).detach().float())
+    assert t["att.w"].shape == (6 * 32, 64) and t["att.b"].shape == (6 * 32,)
+    assert torch.equal(t["att.w"][32:64], gcn.b_conv[0].weight.detach()[:, :, 0, 0])  # rows: theta_0, phi_0, theta_1, ...
+    assert torch.equal(t["att.w"][64:96], gcn.a_conv[1].weight.detach()[:, :, 0, 0])
+    with pytest.raises(ValueError):
+        cs.CoStack([cs.BlockSpec(2, 2, 1, True)], adaptive=True)  # out_channels // 4 == 0, as in the reference
