@@ -139,11 +139,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def kernel_label(path, kname, cout, kblock):
+def kernel_label(path, kname, cout, kblock, workload="cost_gcn"):
     if path != "auto":
         return f"k_{kname}_simt (layer {kblock + 1}, C={cout})"
     if kname == "tcn":
         return (f"k_tc_tcn<{cout}>" if cout == 64 else f"k_tc_tcn2<{cout}> (CTA pairs)") + f" (layer {kblock + 1})"
+    if workload == "coa_gcn":
+        return f"k_tc_agcn C={cout} (layer {kblock + 1}; dense per-skeleton mix, attention kernel timed separately)"
     return f"k_tc_gcn<4> C={cout} (layer {kblock + 1})"
 
 
@@ -321,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "roofline": {
-            "bound": "hbm", "kernel": kernel_label(args.kernel_path, kname, cout, kblock),
+            "bound": "hbm", "kernel": kernel_label(args.kernel_path, kname, cout, kblock, args.workload),
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
             "peak_source": peaks["source"],

@@ -467,7 +467,7 @@ int launch_tc_agcn(cosk_model *m, const TcGcnArgs &args, cudaStream_t s) {
 template <int IC, int V>
 int launch_tc_attn(cosk_model *m, const TcAttnArgs &args, cudaStream_t s) {
   const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
-  CK(launch_k(m, k_tc_attn<IC, V>, dim3(grid), dim3(256), TcAttnCfg<IC, V>::kSmemBytes, s, args));
+  CK(launch_k(m, k_tc_attn<IC, V>, dim3(grid), dim3(384), TcAttnCfg<IC, V>::kSmemBytes, s, args));
   return COSK_OK;
 }
 
@@ -572,7 +572,7 @@ TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, lo
 // possible when both run on the tensor-core kernels, the temporal conv is one of the HBM-bound widths and
 // there are enough tiles to feed both CTA groups.
 bool can_merge(const cosk_model *m, int i) {
-  if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace) return false;
+  if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.graph_conv != COSK_GCONV_PLAIN) return false;
   const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
   const int c = m->cfg.blocks[i].cout;
   if (!b.tc_tcn || !nb.tc_gcn || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;

@@ -1255,11 +1255,11 @@ __global__ void __launch_bounds__(512, 1) k_tc_agcn(const __grid_constant__ TcGc
 // models/a_gcn/a_gcn.py:52-63).  Work item = (token tile, partition i):
 //   mainloop   [theta_i | phi_i] = X [128 x cin] * [Wa_i | Wb_i]^T, 2*IC columns, stacked-B split products
 //              (the hi and lo weight rows of a partition are adjacent in memory: one operand of 4*IC rows);
-//   epilogue   (4 warps, thread = token row) accumulator -> shared memory (theta in a skeleton-padded
+//   epilogue   (2 groups of 4 warps on alternate items, thread = token row) accumulator -> shared memory (theta in a skeleton-padded
 //              layout so a lane reads its skeleton's V values with 16-byte broadcast loads), then per row w:
 //              S[v] = <theta[v], phi[w]> / IC, softmax over v, + (A + graph_attn)_i[v][w], written as the
 //              token's mixing row to the dense scratch k_tc_agcn reads.
-// The next item's MMAs run while the epilogue warps work (two accumulators in TMEM).
+// Group g owns TMEM accumulator g, so two items are in their epilogue while the MMAs of a third are issued.
 // =============================================================================================
 struct TcAttnArgs {
   CUtensorMap tm_x;  // block input ring, box {64, 128}
@@ -1281,11 +1281,14 @@ struct TcAttnCfg {
   static constexpr int kThetaPitch = kSkel * kSkp;             // floats per channel row
   static constexpr int kBBytes = 4 * IC * kBK * 2;             // stacked hi + lo rows
   static constexpr int kStageBytes = 2 * kABytes + kBBytes;
-  static constexpr int kStages = 2;
-  static constexpr int kThetaOff = kStages * (2 * kABytes + 4 * 64 * kBK * 2);  // stages sized for IC = 64: 1024-byte aligned
-  static constexpr int kStageStride = 2 * kABytes + 4 * 64 * kBK * 2;
+  // two epilogue groups work on alternate items, each with its own theta / phi buffers; the widest embedding pays
+  // for them with the second operand stage (its epilogue, not the mainloop, is what bounds the kernel)
+  static constexpr int kStages = IC == 64 ? 1 : 2;
+  static constexpr int kStageStride = 2 * kABytes + 4 * 64 * kBK * 2;  // sized for IC = 64: 1024-byte aligned
+  static constexpr int kThetaOff = kStages * kStageStride;
   static constexpr int kPhiOff = kThetaOff + IC * kThetaPitch * 4;
-  static constexpr int kAdjOff = kPhiOff + IC * kTileRows * 4;
+  static constexpr int kGroupBytes = IC * kThetaPitch * 4 + IC * kTileRows * 4;  // theta + phi of one group
+  static constexpr int kAdjOff = kThetaOff + 2 * kGroupBytes;
   static constexpr int kBiasOff = kAdjOff + (3 * V * V * 4 + 15) / 16 * 16;
   static constexpr int kBarOff = kBiasOff + 6 * IC * 4;
   static constexpr int kSmemBytes = kBarOff + 128 + 1024;
@@ -1340,12 +1343,10 @@ __device__ __forceinline__ void attn_softmax_row(const float *theta_s, const flo
 }
 
 template <int IC, int V>
-__global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAttnArgs a) {
+__global__ void __launch_bounds__(384, 1) k_tc_attn(const __grid_constant__ TcAttnArgs a) {
   using Cfg = TcAttnCfg<IC, V>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  float *theta_s = reinterpret_cast<float *>(smem + Cfg::kThetaOff);  // [IC][kThetaPitch]
-  float *phi_s = reinterpret_cast<float *>(smem + Cfg::kPhiOff);      // [IC][128]
   float *adj_s = reinterpret_cast<float *>(smem + Cfg::kAdjOff);      // [3][V][V]
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);    // [3][2*IC]
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
@@ -1429,11 +1430,15 @@ __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAt
       }
     }
   } else if (warp >= 4) {
+    // two groups of four warps (4..7, 8..11): group g owns accumulator g and takes the items with (it & 1) == g
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool row_ok = row < a.tile_tokens;
     const int sk = row_ok ? row / V : 0, wv = row_ok ? row - sk * V : 0;
     const int th_col = sk * Cfg::kSkp;  // this row's skeleton in the theta buffer
+    float *theta_s = reinterpret_cast<float *>(smem + Cfg::kThetaOff + grp * Cfg::kGroupBytes);  // [IC][kThetaPitch]
+    float *phi_s = reinterpret_cast<float *>(smem + Cfg::kPhiOff + grp * Cfg::kGroupBytes);      // [IC][128]
     bool ok = true;
     int it = 0;
     for (int tile = cta; tile < a.n_tiles; tile += ncta) {
@@ -1441,6 +1446,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAt
       const bool valid = row_ok && tok < a.n_tokens;
       for (int part = 0; part < 3; ++part, ++it) {
         const int acc = it & 1;
+        if (acc != grp) continue;
         // a warp whose wait expired keeps walking the items (named barriers below), it only stops computing
         if (ok) ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
         if (ok) {
@@ -1469,9 +1475,9 @@ __global__ void __launch_bounds__(256, 1) k_tc_attn(const __grid_constant__ TcAt
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[acc]);  // accumulator drained: the next item's MMAs may start
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // theta / phi of the whole tile are in shared memory
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // theta / phi of the whole tile are in shared memory
         if (ok && valid) attn_softmax_row<IC, V>(theta_s, phi_s, adj_s, part, row, th_col, wv, a.dense + tok * a.dense_ld);
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // buffers free for the next item
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // buffers free for the group's next item
       }
     }
   }
