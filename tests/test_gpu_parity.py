@@ -412,3 +412,24 @@ def test_adaptive_kinetics_skeleton_stack(path):
     assert _rel_err(got.cpu(), want) < BLOCK_RTOL, _rel_err(got.cpu(), want)
     if path == "auto":
         assert stack.tensor_core_blocks() == [3, 3]
+
+
+@pytest.mark.parametrize("cls,arch_fn,tag", [
+    (cs.CoStGcn, weights.cost_gcn_arch, "cost_gcn"),
+    (cs.CoStGcnMod, weights.cost_gcn_mod_arch, "cost_gcn_mod"),
+    (cs.CoAGcn, weights.coa_gcn_arch, "coa_gcn"),
+])
+def test_full_size_4096_streams_replica_property(golden, cls, arch_fn, tag):
+    """BASELINE's full size (4096 concurrent streams per GPU) through a size-independent property: the 2-stream
+    parity clip replicated 2048 times must give, for every replica, bit-identical logits -- and those must be the
+    logits the 2-stream run gives, which are checked against the reference-block fixture."""
+    arch, sd, m = _load_model(cls, arch_fn, False)
+    base = weights.make_input((2, 3, 300, 25, 2), seed=11).to(DEV)
+    small = m.forward_steps(base)
+    want = torch.from_numpy(golden[tag][f"{tag}_co_logits"])
+    assert float((small.cpu() - want).abs().max()) <= 1e-3 * max(1.0, float(want.abs().max()) / 16.0)
+    reps = 2048
+    big = m.forward_steps(base.unsqueeze(0).expand(reps, 2, 3, 300, 25, 2).reshape(2 * reps, 3, 300, 25, 2))
+    assert m.device_error() == 0
+    assert tuple(big.shape) == (2 * reps, 60)
+    assert torch.equal(big.view(reps, 2, 60), small.unsqueeze(0).expand(reps, 2, 60))
