@@ -56,6 +56,7 @@ struct BlockW {
   CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half, map_att_w;  // _half: box of cout/2 rows for the CTA-pair kernel
   bool tc_gcn = false, tc_tcn = false;
   bool tc_attn = false;  // adaptive graph conv: attention half on the tcgen05 kernel
+  bool gcn_res_in_mix = false;  // P = 3 plain graph conv: identity residual added by the mix warps (else by the drain warps)
   bool tcn_res_kblock = false;  // tensor-core temporal conv: the residual enters as extra K-blocks of the GEMM (folded
                                 // strided conv, or identity weights for the narrow layers) instead of epilogue loads
   long long n_in = 0, n_out = 0;
@@ -74,7 +75,8 @@ struct ProfRec {
 struct cosk_model {
   cosk_config cfg;
   int num_sms = 148;
-  int gcn_identity_mma = 1;  // identity gcn_residual as a 4th GEMM column group (COSK_GCN_IDENTITY_MMA=0: add input rows instead)
+  int gcn_identity_mma = 3;  // COSK_GCN_IDENTITY_MMA: 1 = identity gcn_residual as a 4th GEMM column group everywhere, 0 = the drain
+                             // warps add the input rows instead, 2 = the mix warps do, 3 = per width (see prepare)
   int tcn_reverse = 1;  // temporal convs walk tiles last-to-first so producer->consumer hand-offs hit L2 (COSK_TCN_REVERSE=0 disables)
   int gcn_single_stage = 1;  // cin = 64 graph convs: 1 operand stage + 4 exchange buffers (COSK_GCN_SINGLE_STAGE=0: 2 stages + 1 buffer)
   int merge = 0;           // temporal conv of block L + graph conv of block L+1 in one cooperative launch (COSK_MERGE=1);
@@ -326,7 +328,11 @@ int prepare(cosk_model *m) {
       // the kernel (identity added from the input rows by the drain warps) exists but measured slower:
       // its row-per-thread global loads cost more load/store-unit cycles than the extra MMA columns.
       // (adaptive: 4 parts need the single-stage layout, so the identity rides along only when one K-block is all there is)
-      const int P = b.gcn_parts = adaptive ? ((res_conv || bc.cin == kBK) ? 4 : 3) : ((res_conv || m->gcn_identity_mma) ? 4 : 3);
+      // mode 3 (default): the identity rides in the GEMM except for the 256-channel layers, where the mix warps have the
+      // slack to add the input rows and the narrower accumulator saves MMA columns and TMEM reads (measured -8 %)
+      const bool ident_mma = m->gcn_identity_mma == 1 || (m->gcn_identity_mma == 3 && bc.cin < 256);
+      b.gcn_res_in_mix = m->gcn_identity_mma >= 2;
+      const int P = b.gcn_parts = adaptive ? ((res_conv || bc.cin == kBK) ? 4 : 3) : ((res_conv || ident_mma) ? 4 : 3);
       std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
       for (int o = 0; o < bc.cout; ++o)
         for (int part = 0; part < P; ++part) {
@@ -535,6 +541,7 @@ TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int
   a.dense = m->d_dense;
   a.dense_ld = 3 * m->dense_vp;
   a.dense_vp = m->dense_vp;
+  a.res_in_mix = b.gcn_res_in_mix ? 1 : 0;
   return a;
 }
 

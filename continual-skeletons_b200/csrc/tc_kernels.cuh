@@ -606,6 +606,7 @@ struct TcGcnArgs {
   // dense[token*dense_ld + partition*dense_vp + source vertex]
   const float *dense;
   int dense_ld, dense_vp;
+  int res_in_mix;  // P = 3 only: 1 = the mix warps add the identity residual rows (epi.r_hi / r_lo), 0 = the drain warps do
 };
 
 template <int P, int STAGES>
@@ -853,7 +854,7 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
     unsigned long long tr_t[4] = {0, 0, 0, 0};
     long long tr_c = 0;
     const long long tr_start = tr ? clock64() : 0;
-    const bool has_res = a.epi.r_hi != nullptr;  // identity gcn_residual (P == 3): own input row, prefetched one chunk ahead
+    const bool has_res = a.epi.r_hi != nullptr && !a.res_in_mix;  // identity gcn_residual (P == 3): own input row, prefetched one chunk ahead
     bool ok = true;
     int it = 0;
     uint32_t xc = 0;  // exchange chunks handed over so far
@@ -989,6 +990,18 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
           const int c0 = pass * 64 + c * kGcnChunk + 4 * cq;
           const uint32_t b = xc % Cfg::kExchBufs;
           const uint32_t use = xc / Cfg::kExchBufs;
+          // identity gcn_residual added here (P == 3, res_in_mix): the two rows' 4 channels, issued before the wait
+          uint2 rh[2] = {make_uint2(0, 0), make_uint2(0, 0)}, rl[2] = {make_uint2(0, 0), make_uint2(0, 0)};
+          if (P == 3 && a.res_in_mix) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const long long tok = tok0 + rows[g];
+              if (rows[g] < a.tile_tokens && tok < a.n_tokens) {
+                rh[g] = __ldg(reinterpret_cast<const uint2 *>(a.epi.r_hi + tok * a.epi.cs_r + c0));
+                rl[g] = __ldg(reinterpret_cast<const uint2 *>(a.epi.r_lo + tok * a.epi.cs_r + c0));
+              }
+            }
+          }
           if (tr) tr_c = clock64();
           ok = ptx::mbar_wait(&xfull[b], use & 1, a.dbg, kDbgEpiExchFull | (xc & 0xffff));
           if (!ok) break;
@@ -1006,6 +1019,15 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
           }
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&xempty[b]);  // planes consumed: the drain warps may refill them
+          if (P == 3 && a.res_in_mix) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              z[g].x += bf16_lo_as_float(rh[g].x) + bf16_lo_as_float(rl[g].x);
+              z[g].y += bf16_hi_as_float(rh[g].x) + bf16_hi_as_float(rl[g].x);
+              z[g].z += bf16_lo_as_float(rh[g].y) + bf16_lo_as_float(rl[g].y);
+              z[g].w += bf16_hi_as_float(rh[g].y) + bf16_hi_as_float(rl[g].y);
+            }
+          }
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const long long tok = tok0 + rows[g];
