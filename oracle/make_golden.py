@@ -52,6 +52,27 @@ ADAPTIVE_BLOCK_CASES = [
 ]
 
 
+# blocks whose graph conv is the spatial self-attention unit of CoS-TR (models/s_tr/s_tr.py:303-476; it works on one
+# frame at a time by construction, so clip and step semantics coincide).  out_channels must be a multiple of 32
+# (dk = out/4 split over 8 heads).  name, cin, cout, stride, residual, temporal_padding, skeleton
+ATTENTION_BLOCK_CASES = [
+    ("s_idres_p4", 32, 32, 1, True, 4, "ntu"),
+    ("s_convres_s2_p4", 8, 32, 2, True, 4, "ntu"),
+    ("s_wide_idres_p4", 64, 64, 1, True, 4, "ntu"),
+    ("s_wide_convres_s2_p4", 64, 128, 2, True, 4, "kinetics"),
+    ("s_wide_idres256_p4", 256, 256, 1, True, 4, "kinetics"),
+]
+
+
+def attention_unit(ref, vertices):
+    """GraphConv factory as models/s_tr/s_tr.py:499-502 / models/cos_tr/cos_tr.py:25-28 build it."""
+
+    def make(in_channels, out_channels, A):
+        return ref.GcnUnitAttention(in_channels, out_channels, A, num_point=vertices)
+
+    return make
+
+
 def per_frame_adaptive(ref):
     """The reference's AdaptiveGraphConvolution applied frame by frame: what forward_step computes, laid
     out as a clip so that the reference's SpatioTemporalBlock can run the temporal part."""
@@ -72,10 +93,18 @@ class RefStack(nn.Module):
         if arch.head:
             self.data_bn = nn.BatchNorm1d(arch.persons * arch.c_in * arch.vertices)
         tp = -1 if arch.padding == 4 else arch.padding
-        kw = {"GraphConv": per_frame_adaptive(ref)} if arch.graph_conv == "adaptive" else {}
+
+        def kw(b):
+            kind = arch.gconv_of(b)
+            if kind == "adaptive":
+                return {"GraphConv": per_frame_adaptive(ref)}
+            if kind == "attention":
+                return {"GraphConv": attention_unit(ref, arch.vertices)}
+            return {}
+
         self.layers = nn.ModuleDict(
             {
-                n.split(".")[-2]: ref.SpatioTemporalBlock(b.cin, b.cout, A, stride=b.stride, residual=b.residual, temporal_padding=tp, **kw)
+                n.split(".")[-2]: ref.SpatioTemporalBlock(b.cin, b.cout, A, stride=b.stride, residual=b.residual, temporal_padding=tp, **kw(b))
                 for n, b in zip(arch.block_names, arch.blocks)
             }
         )
@@ -141,12 +170,36 @@ def adaptive_block_fixtures(ref):
     return out
 
 
+def attention_block_fixtures(ref):
+    out = {}
+    for idx, (name, cin, cout, stride, residual, pad, skel) in enumerate(ATTENTION_BLOCK_CASES):
+        A = ref.ntu_A if skel == "ntu" else ref.kinetics_A
+        V = A.shape[-1]
+        for rnd in (False, True):
+            arch = weights.ArchSpec([BlockSpec(cin, cout, stride, residual, gconv="attention")], padding=pad, head=False,
+                                    block_names=[""], skeleton=skel)
+            sd = weights.make_state_dict(arch, seed=5000 + idx, randomize=rnd)
+            blk = ref.SpatioTemporalBlock(cin, cout, A, stride=stride, residual=residual, temporal_padding=pad,
+                                          GraphConv=attention_unit(ref, V))
+            blk.load_state_dict(sd, strict=True)
+            blk.eval()
+            batch = 1 if "wide" in name else BLOCK_B
+            frames = 14 if "wide" in name else BLOCK_T
+            x = weights.make_input((batch, cin, frames, V), seed=6000 + idx)
+            with torch.no_grad():
+                y = blk(x)
+                g = blk.gcn(x[:, :, :2])
+            out[f"{name}{'_rnd' if rnd else ''}"] = y.numpy()
+            out[f"{name}{'_rnd' if rnd else ''}_gcn"] = g.numpy()
+    return out
+
+
 def model_fixtures(ref, arch_fn, tag, n=2):
     out = {}
     for rnd in (False, True):
         arch = arch_fn()
         sd = weights.make_state_dict(arch, seed=7 if not rnd else 8, randomize=rnd)
-        net = RefStack(ref, arch, ref.ntu_A)
+        net = RefStack(ref, arch, ref.ntu_A if arch.skeleton == "ntu" else ref.kinetics_A)
         missing = net.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
         net.eval()
@@ -184,6 +237,8 @@ def main():
     save("cost_gcn_mod", lambda: model_fixtures(ref, weights.cost_gcn_mod_arch, "cost_gcn_mod"))
     save("coa_blocks", lambda: adaptive_block_fixtures(ref))
     save("coa_gcn", lambda: model_fixtures(ref, weights.coa_gcn_arch, "coa_gcn"))
+    save("cos_blocks", lambda: attention_block_fixtures(ref))
+    save("cos_tr", lambda: model_fixtures(ref, weights.cos_tr_arch, "cos_tr"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

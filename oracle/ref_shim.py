@@ -68,6 +68,12 @@ def load():
     ns.__path__ = [os.path.join(REF_ROOT, "models", "a_gcn")]
     sys.modules["models.a_gcn"] = ns
     importlib.import_module("models.a_gcn.a_gcn")
+    # models/s_tr/s_tr.py:16 pulls the training optimizer mixin; only the class statement of STr needs the name
+    _stub("optimizers", SgdMultiStepLR=type("SgdMultiStepLR", (), {}))
+    ns = types.ModuleType("models.s_tr")
+    ns.__path__ = [os.path.join(REF_ROOT, "models", "s_tr")]
+    sys.modules["models.s_tr"] = ns
+    importlib.import_module("models.s_tr.s_tr")
     sys.modules["models.base"]._cosk_shim = True
     return _namespace()
 
@@ -79,6 +85,7 @@ def _namespace():
         TemporalConvolution=base.TemporalConvolution,
         SpatioTemporalBlock=base.SpatioTemporalBlock,
         AdaptiveGraphConvolution=sys.modules["models.a_gcn.a_gcn"].AdaptiveGraphConvolution,
+        GcnUnitAttention=sys.modules["models.s_tr.s_tr"].GcnUnitAttention,
         init_weights=utils.init_weights,
         ntu_A=sys.modules["datasets.ntu_rgbd"].graph.A,
         kinetics_A=sys.modules["datasets.kinetics"].graph.A,

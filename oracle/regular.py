@@ -51,10 +51,42 @@ def adaptive_graph_conv(x, sd, key):
     return F.relu(total + skip)
 
 
+ATTENTION_HEADS = 8  # Nh default of GcnUnitAttention, never overridden (models/s_tr/s_tr.py:311; cos_tr.py:25-28)
+
+
+def attention_graph_conv(x, sd, key):
+    """GcnUnitAttention.forward with only_attention=True, eval mode (models/s_tr/s_tr.py:417-476) around
+    SpatialAttention.forward (:134-231; relative=False, adjacency=False, drop-connect is training only):
+    per frame, every vertex attends over the V vertices of its skeleton with 8 heads."""
+    B, C, T, V = x.shape
+    y = x.permute(0, 1, 3, 2).reshape(B, C * V, T)
+    y = _bn(y, sd, key + "data_bn.")
+    y = y.reshape(B, C, V, T).permute(0, 1, 3, 2)
+    xa = y.permute(0, 2, 1, 3).reshape(B * T, C, 1, V)
+    qkv = _conv(xa, sd, key + "attention_conv.qkv_conv.")
+    dv = sd[key + "attention_conv.attn_out.weight"].shape[0]
+    dk = (qkv.shape[1] - dv) // 2
+    nh = ATTENTION_HEADS
+    q, k, v = torch.split(qkv, [dk, dk, dv], dim=1)
+    q = q.reshape(B * T, nh, dk // nh, V) * ((dk // nh) ** -0.5)
+    k = k.reshape(B * T, nh, dk // nh, V)
+    v = v.reshape(B * T, nh, dv // nh, V)
+    w = torch.softmax(torch.matmul(q.transpose(2, 3), k), dim=-1)  # (BT, nh, V, V): row i attends over j
+    o = torch.matmul(w, v.transpose(2, 3))  # (BT, nh, V, dvh)
+    o = o.reshape(B * T, nh, 1, V, dv // nh).permute(0, 1, 4, 2, 3).reshape(B * T, dv, 1, V)
+    o = _conv(o, sd, key + "attention_conv.attn_out.")
+    o = o.reshape(B, T, dv, V).permute(0, 2, 1, 3)
+    if C == dv:  # skip_conn and in_channels == out_channels
+        o = o + x
+    return F.relu(_bn(o, sd, key + "bn."))
+
+
 def graph_conv(x, sd, key, per_frame=False):
     """x (B, Cin, T, V) -> (B, Cout, T, V).  models/base.py:260-270; dispatches to the adaptive variant when
     the state_dict holds its embedding convs.  ``per_frame`` evaluates the adaptive attention one frame at a
     time, which is what the continual model does step by step."""
+    if (key + "attention_conv.qkv_conv.weight") in sd:
+        return attention_graph_conv(x, sd, key)
     if (key + "a_conv.0.weight") in sd:
         if per_frame and x.shape[2] > 1:
             return torch.cat([adaptive_graph_conv(x[:, :, t: t + 1], sd, key) for t in range(x.shape[2])], dim=2)

@@ -22,6 +22,7 @@ class BlockSpec:
     cout: int
     stride: int = 1
     residual: bool = True
+    gconv: str = ""  # "" = the stack's ArchSpec.graph_conv; else "plain" / "adaptive" / "attention"
 
     @property
     def res_kind(self):
@@ -46,7 +47,12 @@ class ArchSpec:
     pool_size: int = -1
     pool_padding: int = -1
     block_names: List[str] = field(default_factory=list)
-    graph_conv: str = "plain"  # "plain": GraphConvolution (models/base.py:230-270); "adaptive": models/a_gcn/a_gcn.py:12-69
+    # "plain": GraphConvolution (models/base.py:230-270); "adaptive": models/a_gcn/a_gcn.py:12-69;
+    # "attention": GcnUnitAttention (models/s_tr/s_tr.py:303-476); a block's own BlockSpec.gconv overrides it
+    graph_conv: str = "plain"
+
+    def gconv_of(self, block):
+        return block.gconv or self.graph_conv
 
     def __post_init__(self):
         if not self.block_names:
@@ -91,6 +97,15 @@ def coa_gcn_arch(skeleton="ntu", classes=60, **kw) -> ArchSpec:
     return ArchSpec(stgcn_blocks(strided=True), padding=4, skeleton=skeleton, classes=classes, graph_conv="adaptive", **kw)
 
 
+def cos_tr_arch(skeleton="kinetics", classes=400, **kw) -> ArchSpec:
+    """CoS-TR: CoST-GCN geometry, layers 4-10 with the spatial self-attention unit
+    (models/cos_tr/cos_tr.py:24-41); BASELINE configs[3] quotes it on the 18-joint Kinetics skeleton."""
+    blocks = stgcn_blocks(strided=True)
+    for b in blocks[3:]:
+        b.gconv = "attention"
+    return ArchSpec(blocks, padding=4, skeleton=skeleton, classes=classes, **kw)
+
+
 def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
@@ -113,6 +128,34 @@ def _bn(sd, key, c, scale):
     sd[key + "num_batches_tracked"] = torch.zeros((), dtype=torch.long)
 
 
+def _tail(rng, sd, name, b):
+    """Temporal conv and block residual (models/base.py:291-300,367-374)."""
+    _conv(rng, sd, name + "tcn.t_conv.", b.cout, b.cout, 9, bs=1)
+    _bn(sd, name + "tcn.bn.", b.cout, 1)
+    if b.res_kind == 2:
+        _conv(rng, sd, name + "residual.t_conv.", b.cout, b.cin, 1, bs=1)
+        _bn(sd, name + "residual.bn.", b.cout, 1)
+
+
+def _torch_default_conv(rng, sd, key, cout, cin):
+    """nn.Conv2d's own initialisation (kaiming_uniform with a = sqrt(5)): U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for
+    weight and bias -- the attention unit never re-initialises its convs (models/s_tr/s_tr.py:82-101)."""
+    bound = 1.0 / math.sqrt(cin)
+    sd[key + "weight"] = _t(rng.uniform(-bound, bound, size=(cout, cin, 1, 1)))
+    sd[key + "bias"] = _t(rng.uniform(-bound, bound, size=(cout,)))
+
+
+def _attention_unit(rng, sd, g, b, A, V):
+    """state_dict of GcnUnitAttention(only_attention=True) (models/s_tr/s_tr.py:303-415): data_bn over C*V
+    features, bn, the parameter A, and SpatialAttention's qkv / output convs with dk = out/4, dv = out."""
+    _bn(sd, g + "data_bn.", b.cin * V, 1)
+    _bn(sd, g + "bn.", b.cout, 1)
+    sd[g + "A"] = _t(A)
+    dk, dv = int(b.cout * 0.25), b.cout
+    _torch_default_conv(rng, sd, g + "attention_conv.qkv_conv.", 2 * dk + dv, b.cin)
+    _torch_default_conv(rng, sd, g + "attention_conv.attn_out.", dv, dv)
+
+
 def make_state_dict(arch: ArchSpec, seed: int, randomize: bool = False) -> "OrderedDict[str, torch.Tensor]":
     """Reference-style initial weights (``randomize=False``) or the randomised-BN variant that
     makes the adjacency branch visible."""
@@ -124,11 +167,16 @@ def make_state_dict(arch: ArchSpec, seed: int, randomize: bool = False) -> "Orde
         _bn(sd, "data_bn.", arch.persons * arch.c_in * V, 1)
     for name, b in zip(arch.block_names, arch.blocks):
         g = name + "gcn."
+        kind = arch.gconv_of(b)
+        if kind == "attention":
+            _attention_unit(rng, sd, g, b, A, V)
+            _tail(rng, sd, name, b)
+            continue
         sd[g + "graph_attn"] = torch.ones(3, V, V)
         sd[g + "A"] = _t(A)
         for i in range(3):
             _conv(rng, sd, g + f"g_conv.{i}.", b.cout, b.cin, 1, bs=3)
-        if arch.graph_conv == "adaptive":  # a_gcn.py:14,25-31 (coff_embedding = 4)
+        if kind == "adaptive":  # a_gcn.py:14,25-31 (coff_embedding = 4)
             inter_c = b.cout // 4
             for i in range(3):
                 _conv(rng, sd, g + f"a_conv.{i}.", inter_c, b.cin, 1, bs=1)
@@ -137,11 +185,7 @@ def make_state_dict(arch: ArchSpec, seed: int, randomize: bool = False) -> "Orde
             _conv(rng, sd, g + "gcn_residual.0.", b.cout, b.cin, 1, bs=1)
             _bn(sd, g + "gcn_residual.1.", b.cout, 1)
         _bn(sd, g + "bn.", b.cout, 1e-6)
-        _conv(rng, sd, name + "tcn.t_conv.", b.cout, b.cout, 9, bs=1)
-        _bn(sd, name + "tcn.bn.", b.cout, 1)
-        if b.res_kind == 2:
-            _conv(rng, sd, name + "residual.t_conv.", b.cout, b.cin, 1, bs=1)
-            _bn(sd, name + "residual.bn.", b.cout, 1)
+        _tail(rng, sd, name, b)
     if arch.head:
         c_last = arch.blocks[-1].cout
         sd["fc.weight"] = _t(rng.standard_normal((arch.classes, c_last)) * math.sqrt(2.0 / arch.classes))

@@ -20,5 +20,5 @@ def golden():
 
     return {
         name: np.load(os.path.join(GOLDEN, name + ".npz"))
-        for name in ("adjacency", "blocks", "cost_gcn", "cost_gcn_mod", "coa_blocks", "coa_gcn")
+        for name in ("adjacency", "blocks", "cost_gcn", "cost_gcn_mod", "coa_blocks", "coa_gcn", "cos_blocks", "cos_tr")
     }

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import graphs, ref_shim, regular, step, weights
-from oracle.make_golden import ADAPTIVE_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
+from oracle.make_golden import ADAPTIVE_BLOCK_CASES, ATTENTION_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
 from oracle.weights import ArchSpec, BlockSpec
 
 
@@ -243,3 +243,67 @@ def test_step_model_coa_gcn(golden, rnd):
     co = torch.from_numpy(g["coa_gcn_co_logits" + sfx])
     scale = max(1.0, float(co.abs().max()) / 16)
     assert torch.allclose(out, co, rtol=1e-4, atol=1e-4 * scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# CoS-TR: spatial self-attention unit in layers 4-10
+# ---------------------------------------------------------------------------------------------
+def _attention_case(idx, rnd):
+    name, cin, cout, stride, residual, pad, skel = ATTENTION_BLOCK_CASES[idx]
+    arch = ArchSpec([BlockSpec(cin, cout, stride, residual, gconv="attention")], padding=pad, head=False, block_names=[""], skeleton=skel)
+    sd = weights.make_state_dict(arch, seed=5000 + idx, randomize=rnd)
+    wide = "wide" in name
+    x = weights.make_input((1 if wide else BLOCK_B, cin, 14 if wide else BLOCK_T, arch.vertices), seed=6000 + idx)
+    return name + ("_rnd" if rnd else ""), arch, sd, x
+
+
+@pytest.mark.parametrize("idx", range(len(ATTENTION_BLOCK_CASES)))
+@pytest.mark.parametrize("rnd", [False, True])
+def test_attention_block_vs_golden(golden, idx, rnd):
+    """Restated GcnUnitAttention block (clip form and stepped) against fixtures made by the reference's own
+    GcnUnitAttention + SpatioTemporalBlock on the NTU and Kinetics graphs."""
+    key, arch, sd, x = _attention_case(idx, rnd)
+    spec, p = arch.blocks[0], arch.padding
+    ref = torch.from_numpy(golden["cos_blocks"][key])
+    scale = max(1.0, float(ref.abs().max()))
+    y = regular.st_block(x, sd, "", spec, p)
+    assert y.shape == ref.shape and torch.allclose(y, ref, atol=2e-6 * scale)
+    g = regular.graph_conv(x[:, :, :2], sd, "gcn.")
+    assert torch.allclose(g, torch.from_numpy(golden["cos_blocks"][key + "_gcn"]), atol=2e-6 * scale)
+    blk = step.StepBlock(sd, "", spec, p)
+    emitted = [o for o in (blk.step(x[:, :, t]) for t in range(x.shape[2])) if o is not None]
+    assert len(emitted) == (x.shape[2] - (8 - p) + spec.stride - 1) // spec.stride
+    for j, o in enumerate(emitted):
+        assert torch.allclose(o, ref[:, :, j], atol=2e-6 * scale), (key, j)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree only exists in the build container")
+def test_attention_unit_vs_live_reference():
+    ref = ref_shim.load()
+    for idx in (0, 3):
+        key, arch, sd, x = _attention_case(idx, True)
+        b = arch.blocks[0]
+        A = ref.ntu_A if arch.skeleton == "ntu" else ref.kinetics_A
+        unit = ref.GcnUnitAttention(b.cin, b.cout, A, num_point=arch.vertices)
+        unit.load_state_dict({k[len("gcn."):]: v for k, v in sd.items() if k.startswith("gcn.")}, strict=True)
+        unit.eval()
+        with torch.no_grad():
+            assert torch.allclose(regular.graph_conv(x, sd, "gcn."), unit(x), atol=1e-6)
+
+
+@pytest.mark.parametrize("rnd", [False, True])
+def test_step_model_cos_tr(golden, rnd):
+    """CoSTr on the Kinetics skeleton (V = 18, 400 classes): CoST-GCN's schedule, logits equal to the reference blocks."""
+    g, sfx = golden["cos_tr"], "_rnd" if rnd else ""
+    arch = weights.cos_tr_arch()
+    assert (arch.vertices, arch.receptive_field, arch.stack_stride, arch.stack_padding, arch.pool_size, arch.pool_padding) == (18, 153, 4, 76, 75, 19)
+    assert [arch.gconv_of(b) for b in arch.blocks] == ["plain"] * 3 + ["attention"] * 7
+    sd = weights.make_state_dict(arch, seed=8 if rnd else 7, randomize=rnd)
+    x = weights.make_input((2, 3, 300, 18, 2), seed=11)
+    m = step.StepModel(sd, arch)
+    with torch.no_grad():
+        out = m.forward_steps(x)
+    assert out.shape == (2, 400)
+    assert [i for i, f in enumerate(m.trace) if f[-1]] == [296]
+    co = torch.from_numpy(g["cos_tr_co_logits" + sfx])
+    assert torch.allclose(out, co, rtol=1e-4, atol=1e-4 * max(1.0, float(co.abs().max()) / 16))
