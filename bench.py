@@ -35,8 +35,21 @@ ALGO = {
     # CoA-GCN: same rings and schedule as CoST-GCN; FLOPs scaled by the paper's
     # per-prediction costs, 0.30 G vs 0.27 G (figures/table-2.png)
     "coa_gcn": {"state": 1.408e6, "io": 600 + 240 / 4 + 2048 / 4, "flops": 115.0e6 * 0.30 / 0.27, "warm": 297, "period": 4},
+    # CoS-TR on the 18-joint Kinetics skeleton (BASELINE configs[3]): CoST-GCN's rings
+    # scaled by 18/25 vertices; FLOPs from the paper's 0.16 G per prediction on Kinetics (figures/table-5.png)
+    "cos_tr": {"state": 1.408e6 * 18 / 25, "io": 432 + 1600 / 4 + 2048 / 4, "flops": 0.16e9 / 4 * 2, "warm": 297, "period": 4},
 }
-NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*", "coa_gcn": "CoA-GCN"}
+NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*", "coa_gcn": "CoA-GCN", "cos_tr": "CoS-TR"}
+GEOMETRY = {"cos_tr": (18, 400, "dummy_kin", "Kinetics-400 skeleton")}  # workload -> V, classes, dataset, label
+DATASET, DATA_LABEL = "dummy_ntu", "NTU RGB+D 60 joint stream"
+
+
+def set_geometry(workload):
+    """Vertex count / class count of the workload's dataset (module-level, read by every arm)."""
+    global V, CLASSES, DATASET, DATA_LABEL
+    V, CLASSES, DATASET, DATA_LABEL = GEOMETRY.get(workload, (25, 60, "dummy_ntu", "NTU RGB+D 60 joint stream"))
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches
 # listed in profiles/r1h_dram_bytes_per_launch.csv (ncu, --cache-control none); None where no capture exists.
 NCU_TRAFFIC = {"tcn<64>": 565.0e6, "tcn<128>": 1136.0e6, "tcn<256>": 2322.0e6, "gcn<64>": 68.0e6, "gcn<128>": 146.0e6,
@@ -102,7 +115,8 @@ def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    arch = {"cost_gcn": weights.cost_gcn_arch, "cost_gcn_mod": weights.cost_gcn_mod_arch, "coa_gcn": weights.coa_gcn_arch}[workload]()
+    arch = {"cost_gcn": weights.cost_gcn_arch, "cost_gcn_mod": weights.cost_gcn_mod_arch, "coa_gcn": weights.coa_gcn_arch,
+            "cos_tr": weights.cos_tr_arch}[workload]()
     sd = weights.make_state_dict(arch, seed=0)
     model = step.StepModel(sd, arch)
     frames = [torch.rand(n_streams, C_IN, V, S) for _ in range(4)]
@@ -129,7 +143,7 @@ def run_reference(args, rank, world):
     sample = (f"{n_sample} concurrent streams per step (bounded sample of the {args.streams}-stream workload), steady state "
               f"after {ALGO[args.workload]['warm']} warm frames, oracle/step.py eager torch fp32")
     line = {
-        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU60"), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "p50_ms_per_step": p50, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -146,13 +160,15 @@ def kernel_label(path, kname, cout, kblock, workload="cost_gcn"):
         return (f"k_tc_tcn<{cout}>" if cout == 64 else f"k_tc_tcn2<{cout}> (CTA pairs)") + f" (layer {kblock + 1})"
     if workload == "coa_gcn":
         return f"k_tc_agcn C={cout} (layer {kblock + 1}; dense per-skeleton mix, attention kernel timed separately)"
+    if workload == "cos_tr" and kblock >= 3:
+        return f"attention-unit output conv, k_tc_tcn with one tap, C={cout} (layer {kblock + 1}; qkv + attention timed separately)"
     return f"k_tc_gcn<4> C={cout} (layer {kblock + 1})"
 
 
 def make_config(args, world):
     return {
-        "workload": f"{NAMES[args.workload]} NTU RGB+D 60 joint stream, per-step forward_step, {args.streams} concurrent streams per GPU, "
-                    f"random-init weights, synthetic U[0,1) frames (N,C=3,V=25,S=2)",
+        "workload": f"{NAMES[args.workload]} {DATA_LABEL}, per-step forward_step, {args.streams} concurrent streams per GPU, "
+                    f"random-init weights, synthetic U[0,1) frames (N,C=3,V={V},S=2)",
         "model_variant": args.workload, "streams_per_gpu": args.streams, "streams_total": args.streams * world,
         "V": V, "S": S, "classes": CLASSES, "sharding": f"streams sharded over {world} rank(s), logits all-gathered on emitting steps",
         "l2": "per-step state traffic is GBs (>> 126 MB L2) and 8 distinct input frames are cycled, so no L2 flush is needed",
@@ -167,9 +183,9 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     algo = ALGO[args.workload]
-    cls = {"cost_gcn": cs.CoStGcn, "cost_gcn_mod": cs.CoStGcnMod, "coa_gcn": cs.CoAGcn}[args.workload]
+    cls = {"cost_gcn": cs.CoStGcn, "cost_gcn_mod": cs.CoStGcnMod, "coa_gcn": cs.CoAGcn, "cos_tr": cs.CoSTr}[args.workload]
     torch.manual_seed(0)
-    model = cls({"dataset_name": "dummy_ntu", "forward_mode": "frame", "kernel_path": args.kernel_path})
+    model = cls({"dataset_name": DATASET, "forward_mode": "frame", "kernel_path": args.kernel_path})
     n_local = args.streams
     n_total = n_local * world
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
@@ -234,7 +250,7 @@ def run_ours(args, rank, world, local_rank):
         g_ms, g_n = model.profile_read(1, b)
         t_ms, t_n = model.profile_read(2, b)
         per_block.append({"gcn_ms": g_ms, "gcn_n": g_n, "tcn_ms": t_ms, "tcn_n": t_n})
-        if args.workload == "coa_gcn":
+        if args.workload in ("coa_gcn", "cos_tr"):
             per_block[-1]["attn_ms"], per_block[-1]["attn_n"] = model.profile_read(4, b)
     model.profile(False)
     if world > 1:
@@ -310,10 +326,10 @@ def run_ours(args, rank, world, local_rank):
     k_tf_credit = 2.0 * k_macs / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
     issued_k = (9 * cout + res_k) if kname == "tcn" else 4 * cin
     k_tf_issued = 3 * 2.0 * (tokens * 128.0 / 125.0) * cout * issued_k / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 and not (args.workload == "coa_gcn" and kname == "gcn") else None
+    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 and V == 25 and not (args.workload == "coa_gcn" and kname == "gcn") else None
     step_bytes = algo["state"] + algo["io"]
     line = {
-        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU60"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, f32 accumulate)" if args.kernel_path == "auto" else "f32",
         "data": "synthetic", "config": make_config(args, world),
@@ -363,6 +379,7 @@ def main():
     ap.add_argument("--kernel-path", default="auto", choices=["auto", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    set_geometry(args.workload)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -41,12 +41,18 @@ struct ActBuf {  // token-major split-bf16 activation ring: [slots][plane hi/lo]
 
 struct BlockW {
   // host copies as loaded (BN already folded by the caller)
-  std::vector<float> mix, gcn_w, gcn_b, tcn_w, res_w, tcn_b, att_w, att_b;
+  std::vector<float> mix, gcn_w, gcn_b, tcn_w, res_w, tcn_b, att_w, att_b, sa_scale, sa_shift, sa_qkv_w, sa_qkv_b, sa_skip;
   // device, SIMT format (k-major fp32)
   float *d_gcn_w = nullptr, *d_gcn_b = nullptr, *d_tcn_w = nullptr, *d_res_w = nullptr, *d_tcn_b = nullptr;
   int *d_mix_ptr = nullptr, *d_mix_src = nullptr;
   float *d_mix_val = nullptr;
   float *d_att_w = nullptr, *d_att_b = nullptr, *d_adj = nullptr;  // adaptive graph conv: k-major embedding convs, dense A + graph_attn
+  // self-attention unit: data_bn affine [cin][V], k-major qkv conv; its output conv lives in d_gcn_w / d_gcn_b
+  float *d_sa_scale = nullptr, *d_sa_shift = nullptr, *d_sa_qkv_w = nullptr, *d_sa_qkv_b = nullptr, *d_res_w_sa = nullptr;
+  __nv_bfloat16 *d_sa_w16 = nullptr;  // output conv (+ identity K-block) for the single-tap tcgen05 launch
+  CUtensorMap map_sa_w, map_sa_w_half;
+  bool tc_sa_out = false, sa_res_kblock = false;
+  ActBuf sa;  // attention output rows of the frame in flight (1 slot), operand of the output conv
   int mix_max_nz = 0;
   int gcn_parts = 4;  // accumulator column groups of the tensor-core graph conv (3 or 4)
   int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
@@ -100,6 +106,7 @@ struct cosk_model {
   ActBuf xin;
   float *d_pool_ring = nullptr;
   double *d_pool_sum = nullptr;
+  float *d_qkv = nullptr;    // self-attention unit: q | k | v rows [t_alloc][2*dk + dv] of the frame in flight (fp32)
   float *d_dense = nullptr;  // adaptive graph conv: per-token mixing rows [t_alloc][3][dense_vp] of the frame in flight
   int dense_vp = 0;
   long long pool_n = 0, frame = 0;
@@ -147,7 +154,9 @@ void free_state(cosk_model *m) {
     dfree(b.ring.ptr);
     dfree(b.out.ptr);
     dfree(b.d_tile_cnt);
+    dfree(b.sa.ptr);
   }
+  dfree(m->d_qkv);
   dfree(m->d_pool_ring);
   dfree(m->d_pool_sum);
   dfree(m->d_dense);
@@ -250,7 +259,17 @@ int prepare(cosk_model *m) {
     const cosk_block_cfg &bc = c.blocks[i];
     BlockW &b = m->blk[i];
     const int res_conv = bc.cin != bc.cout ? 1 : 0;
-    const int Kg = (3 + res_conv) * bc.cin, Kt = kTaps * bc.cout;
+    const bool attention = bc.gconv == COSK_GCONV_ATTENTION;
+    const int Kg = attention ? bc.cout : (3 + res_conv) * bc.cin, Kt = kTaps * bc.cout;
+    if (attention) {
+      const int nq = 2 * (bc.cout / 4) + bc.cout;
+      if (b.sa_scale.size() != (size_t)bc.cin * V || b.sa_shift.size() != (size_t)bc.cin * V)
+        return fail(m, COSK_ERR_STATE, "block%d.sa.in_scale / in_shift missing or wrong size", i);
+      if (b.sa_qkv_w.size() != (size_t)nq * bc.cin || b.sa_qkv_b.size() != (size_t)nq)
+        return fail(m, COSK_ERR_STATE, "block%d.sa.qkv.w / qkv.b missing or wrong size", i);
+      if (!res_conv && b.sa_skip.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.sa.skip_scale missing", i);
+      b.mix.assign((size_t)3 * V * V, 0.f);  // the unit does not mix with the adjacency (only_attention)
+    }
     if (b.mix.size() != (size_t)3 * V * V) return fail(m, COSK_ERR_STATE, "block%d.mix missing", i);
     if (b.gcn_w.size() != (size_t)bc.cout * Kg) return fail(m, COSK_ERR_STATE, "block%d.gcn.w missing or wrong size", i);
     if (b.gcn_b.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.gcn.b missing", i);
@@ -258,7 +277,7 @@ int prepare(cosk_model *m) {
     if (b.tcn_b.size() != (size_t)bc.cout) return fail(m, COSK_ERR_STATE, "block%d.tcn.b missing", i);
     if (bc.res_kind == COSK_RES_CONV && b.res_w.size() != (size_t)bc.cout * bc.cin)
       return fail(m, COSK_ERR_STATE, "block%d.res.w missing", i);
-    const bool adaptive = c.graph_conv == COSK_GCONV_ADAPTIVE;
+    const bool adaptive = bc.gconv == COSK_GCONV_ADAPTIVE;
     if (adaptive) {
       const int ic = bc.cout / 4;  // coff_embedding = 4, models/a_gcn/a_gcn.py:13-14
       if (b.att_w.size() != (size_t)6 * ic * bc.cin || b.att_b.size() != (size_t)6 * ic)
@@ -316,7 +335,9 @@ int prepare(cosk_model *m) {
     }
     // tensor-core eligibility + weights
     const bool want_tc = c.path == COSK_PATH_AUTO;
-    if (adaptive)  // dense-mix kernel: instantiated for the two skeleton sizes the reference ships
+    if (attention)
+      b.tc_gcn = false;  // qkv + attention run on CUDA cores this round; the output conv below is the tensor-core part
+    else if (adaptive)  // dense-mix kernel: instantiated for the two skeleton sizes the reference ships
       b.tc_gcn = want_tc && m->agcn_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && (V == 25 || V == 18);
     else
       b.tc_gcn = want_tc && bc.cout % 64 == 0 && bc.cout <= 256 && bc.cin % kBK == 0 && b.mix_max_row12 <= kMixSlots && b.mix_diag0;
@@ -345,6 +366,34 @@ int prepare(cosk_model *m) {
       std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
       if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
+    }
+    if (attention) {
+      std::vector<float> tq = transpose(b.sa_qkv_w.data(), 2 * (bc.cout / 4) + bc.cout, bc.cin);
+      if ((rc = upload(m, b.d_sa_qkv_w, tq.data(), tq.size()))) return rc;
+      if ((rc = upload(m, b.d_sa_qkv_b, b.sa_qkv_b.data(), b.sa_qkv_b.size()))) return rc;
+      if ((rc = upload(m, b.d_sa_scale, b.sa_scale.data(), b.sa_scale.size()))) return rc;
+      if ((rc = upload(m, b.d_sa_shift, b.sa_shift.data(), b.sa_shift.size()))) return rc;
+      // The skip connection is added before the unit's bn, so it enters scaled per channel: a diagonal "residual conv".
+      if (!res_conv) {
+        std::vector<float> diag((size_t)bc.cin * bc.cout, 0.f);  // k-major [cin][cout]
+        for (int r = 0; r < bc.cout; ++r) diag[(size_t)r * bc.cout + r] = b.sa_skip[r];
+        if ((rc = upload(m, b.d_res_w_sa, diag.data(), diag.size()))) return rc;
+      }
+      // output conv on the temporal-conv kernel with a single tap: [W0 | diag(skip scale) K-block on the input rows]
+      b.tc_sa_out = want_tc && tc_width(bc.cout);
+      if (b.tc_sa_out) {
+        b.sa_res_kblock = !res_conv;
+        const int Kr = b.sa_res_kblock ? bc.cin : 0, K0 = bc.cout;
+        std::vector<float> cat((size_t)bc.cout * (K0 + Kr), 0.f);
+        for (int r = 0; r < bc.cout; ++r) {
+          memcpy(&cat[(size_t)r * (K0 + Kr)], &b.gcn_w[(size_t)r * K0], sizeof(float) * K0);
+          if (b.sa_res_kblock) cat[(size_t)r * (K0 + Kr) + K0 + r] = b.sa_skip[r];
+        }
+        std::vector<uint16_t> s16 = split_rows(cat, bc.cout, K0 + Kr);
+        if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_sa_w16), s16.data(), s16.size()))) return rc;
+        if ((rc = make_map(m, &b.map_sa_w, b.d_sa_w16, (uint64_t)(K0 + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout))) return rc;
+        if ((rc = make_map(m, &b.map_sa_w_half, b.d_sa_w16, (uint64_t)(K0 + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout / 2))) return rc;
+      }
     }
     b.tc_attn = adaptive && b.tc_gcn && m->attn_tc && tc_width(bc.cout);
     if (b.tc_attn) {
@@ -555,6 +604,7 @@ TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, lo
   for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
   a.res_row = (int)in.row_hi(res_slot);
   a.t_alloc = (int)m->t_alloc;
+  a.n_taps = kTaps;
   a.kb_per_tap = bc.cout / kBK;
   a.kb_res = b.tcn_res_kblock ? bc.cin / kBK : 0;
   a.n_tiles = m->n_tiles;
@@ -579,7 +629,7 @@ TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, lo
 // possible when both run on the tensor-core kernels, the temporal conv is one of the HBM-bound widths and
 // there are enough tiles to feed both CTA groups.
 bool can_merge(const cosk_model *m, int i) {
-  if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.graph_conv != COSK_GCONV_PLAIN) return false;
+  if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.blocks[i + 1].gconv != COSK_GCONV_PLAIN) return false;
   const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
   const int c = m->cfg.blocks[i].cout;
   if (!b.tc_tcn || !nb.tc_gcn || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
@@ -625,13 +675,124 @@ int run_tcn_gcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long 
   return COSK_OK;
 }
 
+// Self-attention unit of CoS-TR (GcnUnitAttention, only_attention): qkv conv on the data_bn-normalised frame, 8-head
+// attention over the vertices of each skeleton, then the output conv + bn + skip + ReLU -- the last one is the
+// temporal-conv kernel run with a single tap on the attention rows.
+int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, cudaStream_t s) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  const int dk = bc.cout / 4, dv = bc.cout, nq = 2 * dk + dv;
+  int rc;
+  {
+    SaQkvArgs a;
+    a.x_hi = in.hi(in_slot);
+    a.x_lo = in.lo(in_slot);
+    a.cs_in = in.cs;
+    a.cin = bc.cin;
+    a.in_scale = b.d_sa_scale;
+    a.in_shift = b.d_sa_shift;
+    a.w = b.d_sa_qkv_w;
+    a.bias = b.d_sa_qkv_b;
+    a.nq = nq;
+    a.V = m->cfg.vertices;
+    a.n_tokens = m->n_tokens;
+    a.tile_tokens = m->tile_tokens;
+    a.qkv = m->d_qkv;
+    dim3 grid(m->n_tiles, (nq + kSimtN - 1) / kSimtN);
+    CK(launch_k(m, k_sa_qkv, grid, dim3(256), 0, s, a));
+    m->launches++;
+  }
+  {
+    SaAttnArgs a;
+    a.qkv = m->d_qkv;
+    a.dk = dk;
+    a.dv = dv;
+    a.heads = 8;  // Nh of GcnUnitAttention, never overridden by the reference (models/s_tr/s_tr.py:311)
+    a.V = m->cfg.vertices;
+    a.n_tokens = m->n_tokens;
+    a.tile_tokens = m->tile_tokens;
+    a.y_hi = b.sa.hi(0);
+    a.y_lo = b.sa.lo(0);
+    a.cs_out = b.sa.cs;
+    CK(launch_k(m, k_sa_attn, dim3(m->n_tiles), dim3(128), 0, s, a));
+    m->launches++;
+  }
+  if ((rc = prof_mark(m, 1, i, s))) return rc;
+  const bool skip = bc.cin == bc.cout;  // skip_conn and in_channels == out_channels (s_tr.py:464-467)
+  if (b.tc_sa_out) {
+    TcTcnArgs a;
+    a.tm_ring = b.sa.map;
+    a.tm_res = b.sa_res_kblock ? in.map : b.sa.map;
+    a.tm_w = b.map_sa_w;
+    for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.sa.row_hi(0);
+    a.res_row = (int)in.row_hi(in_slot);
+    a.t_alloc = (int)m->t_alloc;
+    a.n_taps = 1;
+    a.kb_per_tap = bc.cout / kBK;
+    a.kb_res = b.sa_res_kblock ? bc.cin / kBK : 0;
+    a.n_tiles = m->n_tiles;
+    a.tile_tokens = m->tile_tokens;
+    a.reverse = 0;
+    a.n_tokens = m->n_tokens;
+    a.epi.bias = b.d_gcn_b;
+    a.epi.r_hi = nullptr;  // the scaled skip connection is the K-block above
+    a.epi.r_lo = nullptr;
+    a.epi.cs_r = in.cs;
+    a.epi.y_hi = b.ring.hi(ring_slot);
+    a.epi.y_lo = b.ring.lo(ring_slot);
+    a.epi.cs_out = b.ring.cs;
+    a.tile_cnt = nullptr;
+    a.trace = nullptr;
+    a.dbg = m->d_dbg;
+    const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
+    if (pair) {
+      if (bc.cout > 128) a.tm_w = b.map_sa_w_half;
+      if (bc.cout == 64) rc = launch_tc_tcn2<64>(m, a, s);
+      else if (bc.cout == 128) rc = launch_tc_tcn2<128>(m, a, s);
+      else rc = launch_tc_tcn2<256>(m, a, s);
+    } else {
+      if (bc.cout == 64) rc = launch_tc_tcn<64>(m, a, s);
+      else if (bc.cout == 128) rc = launch_tc_tcn<128>(m, a, s);
+      else rc = launch_tc_tcn<256>(m, a, s);
+    }
+    if (rc) return rc;
+  } else {
+    TcnArgs a;
+    for (int k = 0; k < kTaps; ++k) {
+      a.tap_hi[k] = b.sa.hi(0);
+      a.tap_lo[k] = b.sa.lo(0);
+    }
+    a.n_taps = 1;
+    a.cs = b.sa.cs;
+    a.c = bc.cout;
+    a.w = b.d_gcn_w;
+    a.r_hi = in.hi(in_slot);
+    a.r_lo = in.lo(in_slot);
+    a.cs_r = in.cs;
+    a.cr = bc.cin;
+    a.res_kind = skip ? COSK_RES_CONV : COSK_RES_NONE;  // diag(skip scale) as a 1x1 "conv" on the input rows
+    a.w_r = b.d_res_w_sa;
+    a.bias = b.d_gcn_b;
+    a.y_hi = b.ring.hi(ring_slot);
+    a.y_lo = b.ring.lo(ring_slot);
+    a.cs_out = b.ring.cs;
+    a.n_tokens = m->n_tokens;
+    a.tile_tokens = m->tile_tokens;
+    dim3 grid(m->n_tiles, (bc.cout + kSimtN - 1) / kSimtN);
+    CK(launch_k(m, k_tcn_simt, grid, dim3(256), 0, s, a));
+  }
+  m->launches++;
+  return COSK_OK;
+}
+
 int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, cudaStream_t s) {
   const cosk_block_cfg &bc = m->cfg.blocks[i];
   BlockW &b = m->blk[i];
   const int res_conv = bc.cin != bc.cout ? 1 : 0;
-  const bool adaptive = m->cfg.graph_conv == COSK_GCONV_ADAPTIVE;
-  int rc = prof_mark(m, adaptive ? 4 : 1, i, s);
+  const bool adaptive = bc.gconv == COSK_GCONV_ADAPTIVE;
+  int rc = prof_mark(m, bc.gconv != COSK_GCONV_PLAIN ? 4 : 1, i, s);
   if (rc) return rc;
+  if (bc.gconv == COSK_GCONV_ATTENTION) return run_attention_unit(m, i, in, in_slot, ring_slot, s);
   if (adaptive && b.tc_attn) {
     TcAttnArgs t;
     t.tm_x = in.map;
@@ -771,6 +932,7 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
       a.tap_hi[k] = b.ring.hi(tap_slot[k]);
       a.tap_lo[k] = b.ring.lo(tap_slot[k]);
     }
+    a.n_taps = kTaps;
     a.cs = b.ring.cs;
     a.c = bc.cout;
     a.w = b.d_tcn_w;
@@ -905,8 +1067,6 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (cfg->n_blocks < 1 || cfg->n_blocks > COSK_MAX_BLOCKS) return COSK_ERR_ARG;
   if (cfg->vertices < 1 || cfg->vertices > kTileRows || cfg->persons < 1 || cfg->c_in < 1) return COSK_ERR_ARG;
   if (cfg->padding != 0 && cfg->padding != 4) return COSK_ERR_ARG;
-  if (cfg->graph_conv != COSK_GCONV_PLAIN && cfg->graph_conv != COSK_GCONV_ADAPTIVE) return COSK_ERR_ARG;
-  if (cfg->graph_conv == COSK_GCONV_ADAPTIVE && cfg->vertices > kAttnMaxV) return COSK_ERR_ARG;
   if (cfg->classes > 0 && (cfg->pool_size < 1 || cfg->pool_padding < 0 || cfg->pool_padding >= cfg->pool_size))
     return COSK_ERR_ARG;
   int prev = cfg->c_in;
@@ -915,7 +1075,11 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
     if (b.cin != prev || b.cout < 1 || (b.stride != 1 && b.stride != 2)) return COSK_ERR_ARG;
     if (b.res_kind == COSK_RES_IDENTITY && (b.cin != b.cout || b.stride != 1)) return COSK_ERR_ARG;
     if (b.res_kind < 0 || b.res_kind > 2) return COSK_ERR_ARG;
-    if (cfg->graph_conv == COSK_GCONV_ADAPTIVE && (b.cout < 4 || b.cout / 4 > kAttnMaxInter)) return COSK_ERR_ARG;
+    if (b.gconv < COSK_GCONV_PLAIN || b.gconv > COSK_GCONV_ATTENTION) return COSK_ERR_ARG;
+    if (b.gconv != COSK_GCONV_PLAIN && cfg->vertices > kAttnMaxV) return COSK_ERR_ARG;
+    if (b.gconv == COSK_GCONV_ADAPTIVE && (b.cout < 4 || b.cout / 4 > kAttnMaxInter)) return COSK_ERR_ARG;
+    // 8 heads over dk = cout/4 and dv = cout channels (models/s_tr/s_tr.py:72-78), head widths the kernel holds in registers
+    if (b.gconv == COSK_GCONV_ATTENTION && (b.cout % 32 != 0 || b.cout / 32 > kSaMaxDkh || b.cout / 8 > kSaMaxDvh)) return COSK_ERR_ARG;
     prev = b.cout;
   }
   cosk_model *m = new cosk_model();
@@ -995,6 +1159,12 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_gcn_w16);
     dfree(b.d_tcn_w16);
     dfree(b.d_att_w16);
+    dfree(b.d_sa_scale);
+    dfree(b.d_sa_shift);
+    dfree(b.d_sa_qkv_w);
+    dfree(b.d_sa_qkv_b);
+    dfree(b.d_sa_w16);
+    dfree(b.d_res_w_sa);
   }
   dfree(m->d_bn_scale);
   dfree(m->d_bn_shift);
@@ -1030,6 +1200,11 @@ int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t
     else if (f == "tcn.b") b.tcn_b = v;
     else if (f == "att.w") b.att_w = v;
     else if (f == "att.b") b.att_b = v;
+    else if (f == "sa.in_scale") b.sa_scale = v;
+    else if (f == "sa.in_shift") b.sa_shift = v;
+    else if (f == "sa.qkv.w") b.sa_qkv_w = v;
+    else if (f == "sa.qkv.b") b.sa_qkv_b = v;
+    else if (f == "sa.skip_scale") b.sa_skip = v;
     else return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
   } else {
     return fail(m, COSK_ERR_ARG, "unknown tensor %s", name);
@@ -1069,7 +1244,22 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
     CK(cudaMalloc(&m->d_pool_sum, (size_t)n_streams * cl * sizeof(double)));
     m->state_bytes += (int64_t)((size_t)c.pool_size * n_streams * cl * sizeof(float) + (size_t)n_streams * cl * sizeof(double));
   }
-  if (c.graph_conv == COSK_GCONV_ADAPTIVE) {
+  bool any_adaptive = false;
+  int max_nq = 0;
+  for (int i = 0; i < c.n_blocks; ++i) {
+    any_adaptive |= c.blocks[i].gconv == COSK_GCONV_ADAPTIVE;
+    if (c.blocks[i].gconv == COSK_GCONV_ATTENTION) {
+      max_nq = std::max(max_nq, 2 * (c.blocks[i].cout / 4) + c.blocks[i].cout);
+      if ((rc = alloc_act(m, m->blk[i].sa, 1, c.blocks[i].cout))) return rc;
+      CK(cudaMemset(m->blk[i].sa.ptr, 0, m->blk[i].sa.bytes()));
+    }
+  }
+  if (max_nq) {
+    const size_t bytes = (size_t)m->t_alloc * max_nq * sizeof(float);
+    CK(cudaMalloc(&m->d_qkv, bytes));
+    m->state_bytes += (int64_t)bytes;  // scratch, counted in the footprint
+  }
+  if (any_adaptive) {
     m->dense_vp = round_up(c.vertices, 4);
     const size_t bytes = (size_t)m->t_alloc * 3 * m->dense_vp * sizeof(float);
     CK(cudaMalloc(&m->d_dense, bytes));
@@ -1149,7 +1339,7 @@ int64_t cosk_launch_count(const cosk_model *m) { return m ? m->launches : 0; }
 
 int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block) {
   if (!m || block < 0 || block >= m->cfg.n_blocks) return COSK_ERR_ARG;
-  return (m->blk[block].tc_gcn ? 1 : 0) | (m->blk[block].tc_tcn ? 2 : 0);
+  return ((m->blk[block].tc_gcn || m->blk[block].tc_sa_out) ? 1 : 0) | (m->blk[block].tc_tcn ? 2 : 0);
 }
 
 int cosk_device_error(cosk_model *m, uint32_t *code) {

@@ -368,8 +368,139 @@ __global__ void __launch_bounds__(256) k_agcn_attn(AttnArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spatial self-attention unit (GcnUnitAttention with only_attention, models/s_tr/s_tr.py:417-476), two kernels
+// in front of the output conv (which is k_tcn_simt / k_tc_tcn with a single tap):
+//   k_sa_qkv:  qkv = Wqkv (data_bn(x)) + b for one token tile x 64 columns, fp32 -> scratch [token][2*dk + dv]
+//   k_sa_attn: per token row i and head h:  w_j = softmax_j <q_i, k_j>,  out_i = sum_j w_j v_j  over the V vertices
+//              of the row's skeleton -> split-bf16 rows [token][dv] (the output conv's operand)
+// ---------------------------------------------------------------------------------------------
+struct SaQkvArgs {
+  const __nv_bfloat16 *x_hi, *x_lo;
+  int cs_in, cin;
+  const float *in_scale, *in_shift;  // [cin][V]
+  const float *w;                    // [cin][nq] k-major, nq = 2*dk + dv
+  const float *bias;                 // [nq]
+  int nq, V;
+  long long n_tokens;
+  int tile_tokens;
+  float *qkv;  // [token][nq]
+};
+
+__global__ void __launch_bounds__(256) k_sa_qkv(SaQkvArgs a) {
+  __shared__ __align__(16) float Xs[kSimtK][kTileRows];
+  __shared__ __align__(16) float Bs[kSimtK][kSimtN];
+  pdl_trigger();
+  pdl_wait();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  const int n0 = blockIdx.y * kSimtN;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < a.cin; c0 += kSimtK) {
+    __syncthreads();
+    {  // rows with the per-(channel, vertex) affine of data_bn applied
+      const int row = threadIdx.x >> 1;
+      const int half = (threadIdx.x & 1) * 8;
+      const bool ok = row < rows_valid;
+      const long long base = (tok0 + row) * a.cs_in;
+      const int wv = row % a.V;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + half + j;
+        float v = 0.f;
+        if (ok && c < a.cin) v = join_bf16(a.x_hi[base + c], a.x_lo[base + c]) * a.in_scale[c * a.V + wv] + a.in_shift[c * a.V + wv];
+        Xs[half + j][row] = v;
+      }
+    }
+    simt_load_w(Bs, a.w, a.nq, c0, min(kSimtK, a.cin - c0), n0, a.nq);
+    __syncthreads();
+    simt_mma_chunk(acc, Xs, Bs, ty, tx);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = ty * 8 + i;
+    if (row >= rows_valid) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < a.nq) a.qkv[(tok0 + row) * a.nq + n] = acc[i][j] + a.bias[n];
+    }
+  }
+}
+
+struct SaAttnArgs {
+  const float *qkv;  // [token][2*dk + dv]
+  int dk, dv, heads, V;
+  long long n_tokens;
+  int tile_tokens;
+  __nv_bfloat16 *y_hi, *y_lo;  // [token][cs_out]
+  int cs_out;
+};
+
+constexpr int kSaMaxDkh = 8;   // dk / heads of a 256-channel unit
+constexpr int kSaMaxDvh = 32;  // dv / heads
+
+// one token tile per CTA, thread = token row; k and v of the current head staged in shared memory
+__global__ void __launch_bounds__(128) k_sa_attn(SaAttnArgs a) {
+  __shared__ float ks[kTileRows][kSaMaxDkh + 1];
+  __shared__ float vs[kTileRows][kSaMaxDvh + 1];
+  pdl_trigger();
+  pdl_wait();
+  const int row = threadIdx.x;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  const bool valid = row < rows_valid;
+  const int nq = 2 * a.dk + a.dv, dkh = a.dk / a.heads, dvh = a.dv / a.heads;
+  const int sk0 = valid ? row - row % a.V : 0;
+  const float *mine = a.qkv + (tok0 + row) * nq;
+  for (int h = 0; h < a.heads; ++h) {
+    __syncthreads();
+    if (valid) {
+      for (int d = 0; d < dkh; ++d) ks[row][d] = mine[a.dk + h * dkh + d];
+      for (int d = 0; d < dvh; ++d) vs[row][d] = mine[2 * a.dk + h * dvh + d];
+    }
+    __syncthreads();
+    if (!valid) continue;
+    float q[kSaMaxDkh];
+#pragma unroll
+    for (int d = 0; d < kSaMaxDkh; ++d) q[d] = d < dkh ? mine[h * dkh + d] : 0.f;
+    float w[kAttnMaxV];
+    float mx = -INFINITY;
+    for (int j = 0; j < a.V; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kSaMaxDkh; ++d)
+        if (d < dkh) s = fmaf(q[d], ks[sk0 + j][d], s);
+      w[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < a.V; ++j) {
+      w[j] = expf(w[j] - mx);
+      sum += w[j];
+    }
+    const float inv = 1.0f / sum;
+    for (int d = 0; d < dvh; ++d) {
+      float o = 0.f;
+      for (int j = 0; j < a.V; ++j) o = fmaf(w[j] * inv, vs[sk0 + j][d], o);
+      __nv_bfloat16 hh, ll;
+      split_bf16(o, hh, ll);
+      a.y_hi[(tok0 + row) * a.cs_out + h * dvh + d] = hh;
+      a.y_lo[(tok0 + row) * a.cs_out + h * dvh + d] = ll;
+    }
+  }
+}
+
 struct TcnArgs {
   const __nv_bfloat16 *tap_hi[kTaps], *tap_lo[kTaps];  // oldest .. newest ring slots
+  int n_taps;                                           // kTaps; 1 when the kernel serves as the attention unit's output conv
   int cs, c;                                            // row stride / channels of the ring
   const float *w;                                       // [9*c][c] k-major (k = tap*c + ci), BN folded
   const __nv_bfloat16 *r_hi, *r_lo;                     // block input of 4 executions ago
@@ -400,9 +531,9 @@ __global__ void __launch_bounds__(256) k_tcn_simt(TcnArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int segs = kTaps + (a.res_kind == 2 ? 1 : 0);
+  const int segs = a.n_taps + (a.res_kind == 2 ? 1 : 0);
   for (int seg = 0; seg < segs; ++seg) {
-    const bool is_res = seg == kTaps;
+    const bool is_res = seg == a.n_taps;
     const __nv_bfloat16 *hi = is_res ? a.r_hi : a.tap_hi[seg];
     const __nv_bfloat16 *lo = is_res ? a.r_lo : a.tap_lo[seg];
     const int cs = is_res ? a.cs_r : a.cs;

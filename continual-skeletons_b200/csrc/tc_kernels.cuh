@@ -151,6 +151,7 @@ struct TcTcnArgs {
   int tap_row[kTaps];   // first row of the hi plane of each tap's slot (oldest .. newest)
   int res_row;          // first row of the hi plane of the residual slot
   int t_alloc;          // rows per plane
+  int n_taps;           // kTaps; 1 when the kernel serves as the output conv of the self-attention unit (operand = tap_row[0])
   int kb_per_tap;       // C / 64
   int kb_res;           // Cr / 64 when res_kind == 2 else 0
   int n_tiles, tile_tokens;
@@ -233,7 +234,7 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
-  const int nkb = kTaps * a.kb_per_tap + a.kb_res;
+  const int nkb = a.n_taps * a.kb_per_tap + a.kb_res;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -254,14 +255,14 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
           ptx::mbar_arrive_expect_tx(&afull[pa.stage], 2 * kABytes);
           const CUtensorMap *tm;
           int c0, row;
-          if (kb < kTaps * a.kb_per_tap) {
+          if (kb < a.n_taps * a.kb_per_tap) {
             const int tap = kb / a.kb_per_tap;
             tm = &a.tm_ring;
             c0 = (kb - tap * a.kb_per_tap) * kBK;
             row = a.tap_row[tap] + tok0;
           } else {
             tm = &a.tm_res;
-            c0 = (kb - kTaps * a.kb_per_tap) * kBK;
+            c0 = (kb - a.n_taps * a.kb_per_tap) * kBK;
             row = a.res_row + tok0;
           }
           // ring history and delayed residual are read once per step: stream them (evict-first) so the
@@ -454,7 +455,7 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  const int nkb = kTaps * a.kb_per_tap + a.kb_res;
+  const int nkb = a.n_taps * a.kb_per_tap + a.kb_res;
   const int n_pairs = (a.n_tiles + 1) / 2;
 
   if (warp == 0) {
@@ -472,14 +473,14 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
           const uint32_t fa = ptx::mapa_u32(ptx::smem_u32(&afull[pa.stage]), 0);
           const CUtensorMap *tm;
           int c0, row;
-          if (kb < kTaps * a.kb_per_tap) {
+          if (kb < a.n_taps * a.kb_per_tap) {
             const int tap = kb / a.kb_per_tap;
             tm = &a.tm_ring;
             c0 = (kb - tap * a.kb_per_tap) * kBK;
             row = a.tap_row[tap] + tok0;
           } else {
             tm = &a.tm_res;
-            c0 = (kb - kTaps * a.kb_per_tap) * kBK;
+            c0 = (kb - a.n_taps * a.kb_per_tap) * kBK;
             row = a.res_row + tok0;
           }
           ptx::tma_load_2d_pair_hint(sa, tm, fa, c0, row, ptx::kEvictFirst);
@@ -833,7 +834,6 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const int n_pass = a.cout / 64;
-  const int nkb = a.cin / kBK;
   constexpr int kChunks = 64 / kGcnChunk;
 
   if (warp == 0) {

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 ROOT = os.path.dirname(PKG_DIR)
 MAX_BLOCKS = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -25,7 +25,8 @@ class CoskError(RuntimeError):
 
 
 class BlockCfg(ctypes.Structure):
-    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("stride", ctypes.c_int32), ("res_kind", ctypes.c_int32)]
+    _fields_ = [("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("stride", ctypes.c_int32), ("res_kind", ctypes.c_int32),
+                ("gconv", ctypes.c_int32)]
 
 
 class Config(ctypes.Structure):
@@ -34,7 +35,6 @@ class Config(ctypes.Structure):
         ("c_in", ctypes.c_int32), ("n_blocks", ctypes.c_int32), ("padding", ctypes.c_int32),
         ("classes", ctypes.c_int32), ("pool_size", ctypes.c_int32), ("pool_padding", ctypes.c_int32),
         ("data_bn", ctypes.c_int32), ("device", ctypes.c_int32), ("path", ctypes.c_int32),
-        ("graph_conv", ctypes.c_int32),
         ("blocks", BlockCfg * MAX_BLOCKS),
     ]
 

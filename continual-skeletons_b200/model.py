@@ -25,11 +25,16 @@ BN_EPS = 1e-5
 KT = 9
 
 
-class BlockSpec(namedtuple("BlockSpec", "cin cout stride residual")):
-    """One CoSpatioTemporalBlock (models/base.py:390-446)."""
+GCONV_KINDS = {"plain": 0, "adaptive": 1, "attention": 2}  # enum cosk_graph_conv
 
-    def __new__(cls, cin, cout, stride=1, residual=True):
-        return super().__new__(cls, int(cin), int(cout), int(stride), bool(residual))
+
+class BlockSpec(namedtuple("BlockSpec", "cin cout stride residual gconv")):
+    """One CoSpatioTemporalBlock (models/base.py:390-446).  ``gconv``: which graph conv it holds -- "plain"
+    (GraphConvolution), "adaptive" (AdaptiveGraphConvolution), "attention" (GcnUnitAttention); "" takes the
+    stack's default."""
+
+    def __new__(cls, cin, cout, stride=1, residual=True, gconv=""):
+        return super().__new__(cls, int(cin), int(cout), int(stride), bool(residual), str(gconv))
 
     @property
     def res_kind(self):
@@ -126,6 +131,25 @@ def _agcn_params(cin, cout, A, coff_embedding=4):
     return g
 
 
+def _sa_params(cin, cout, A, V, heads=8):
+    """Parameters of GcnUnitAttention(only_attention=True) + its SpatialAttention (models/s_tr/s_tr.py:303-415,
+    26-101): per-(channel, vertex) input BatchNorm, qkv and output 1x1 convs with PyTorch's default init (the
+    reference never re-initialises them), output BatchNorm, and the (unused here) parameter A."""
+    dk, dv = int(cout * 0.25), cout
+    if dk % heads or dv % heads or dk == 0:
+        raise ValueError("GcnUnitAttention needs out_channels to be a multiple of 32 (dk = out/4 over 8 heads)")
+    g = _Node()
+    g.data_bn = nn.BatchNorm1d(cin * V)
+    g.bn = nn.BatchNorm2d(cout)
+    g.A = nn.Parameter(torch.from_numpy(np.asarray(A, dtype=np.float32)).clone())
+    att = _Node()
+    att.qkv_conv = nn.Conv2d(cin, 2 * dk + dv, 1)
+    att.attn_out = nn.Conv2d(dv, dv, 1)
+    g.attention_conv = att
+    g.heads, g.dk, g.dv = heads, dk, dv
+    return g
+
+
 def _tconv_params(cin, cout, k, stride, pad):
     """Parameters of (Co)TemporalConvolution (models/base.py:279-334)."""
     t = _Node()
@@ -136,11 +160,14 @@ def _tconv_params(cin, cout, k, stride, pad):
     return t
 
 
-def _block_params(spec, A, pad, adaptive=False):
+def _block_params(spec, A, pad, gconv="plain"):
     """Module tree with the state_dict keys of CoSpatioTemporalBlock (models/base.py:412-446):
     plain ``gcn.* / tcn.*`` without residual, ``0.1.gcn.* / 0.1.tcn.*`` under a residual wrapper,
     plus ``0.0.residual.*`` for the strided 1x1 residual conv."""
-    gcn = (_agcn_params if adaptive else _gcn_params)(spec.cin, spec.cout, A)
+    if gconv == "attention":
+        gcn = _sa_params(spec.cin, spec.cout, A, np.asarray(A).shape[-1])
+    else:
+        gcn = (_agcn_params if gconv == "adaptive" else _gcn_params)(spec.cin, spec.cout, A)
     tcn = _tconv_params(spec.cout, spec.cout, KT, spec.stride, pad)
     blk = _Node()
     if spec.res_kind == 0:
@@ -169,6 +196,10 @@ def _fold_bn(bn):
 def _folded_block_tensors(blk, spec):
     """BN-folded fp32 tensors in the layout cosk_load_weights documents (include/cosk.h)."""
     gcn, tcn, res = blk._cosk_parts
+    if hasattr(gcn, "attention_conv"):
+        out = _folded_attention_unit(gcn)
+        out.update(_folded_temporal(tcn, res, spec))
+        return {k: v.float().contiguous().cpu() for k, v in out.items()}
     s, t = _fold_bn(gcn.bn)
     ws = [conv.weight.detach().double()[:, :, 0, 0] * s[:, None] for conv in gcn.g_conv]
     bias = s * sum(conv.bias.detach().double() for conv in gcn.g_conv) + t
@@ -188,6 +219,13 @@ def _folded_block_tensors(blk, spec):
         convs = [c for pair in zip(gcn.a_conv, gcn.b_conv) for c in pair]
         out["att.w"] = torch.cat([c.weight.detach().double()[:, :, 0, 0] for c in convs], dim=0)
         out["att.b"] = torch.cat([c.bias.detach().double() for c in convs], dim=0)
+    out.update(_folded_temporal(tcn, res, spec))
+    return {k: v.float().contiguous().cpu() for k, v in out.items()}
+
+
+def _folded_temporal(tcn, res, spec):
+    """Temporal conv + block residual conv with their BatchNorms folded (models/base.py:307-334, 412-446)."""
+    out = {}
     s, t = _fold_bn(tcn.bn)
     w = tcn.t_conv.weight.detach().double()[:, :, :, 0].permute(0, 2, 1) * s[:, None, None]  # [cout][tap][cin]
     out["tcn.w"] = w.reshape(spec.cout, KT * spec.cout)
@@ -197,7 +235,29 @@ def _folded_block_tensors(blk, spec):
         out["res.w"] = res.t_conv.weight.detach().double()[:, :, 0, 0] * sr[:, None]
         bias = bias + sr * res.t_conv.bias.detach().double() + tr
     out["tcn.b"] = bias
-    return {k: v.float().contiguous().cpu() for k, v in out.items()}
+    return out
+
+
+def _folded_attention_unit(gcn):
+    """Tensors of a COSK_GCONV_ATTENTION block (include/cosk.h): the unit's data_bn as a per-(channel, vertex) affine,
+    the qkv conv with the query scale dkh^-0.5 folded into its q rows (models/s_tr/s_tr.py:251-252), and the output
+    conv with the unit's bn folded."""
+    s_in, t_in = _fold_bn(gcn.data_bn)
+    att = gcn.attention_conv
+    wq = att.qkv_conv.weight.detach().double()[:, :, 0, 0].clone()
+    bq = att.qkv_conv.bias.detach().double().clone()
+    scale = float(gcn.dk // gcn.heads) ** -0.5
+    wq[: gcn.dk] *= scale
+    bq[: gcn.dk] *= scale
+    s, t = _fold_bn(gcn.bn)
+    return {
+        "sa.in_scale": s_in, "sa.in_shift": t_in,
+        "sa.qkv.w": wq, "sa.qkv.b": bq,
+        "gcn.w": att.attn_out.weight.detach().double()[:, :, 0, 0] * s[:, None],
+        "gcn.b": s * att.attn_out.bias.detach().double() + t,
+        # the skip connection is added BEFORE the unit's bn (s_tr.py:464-470), so it carries the bn scale
+        "sa.skip_scale": s,
+    }
 
 
 # ---------------------------------------------------------------------------------------------
@@ -246,7 +306,11 @@ class _CoBase(nn.Module):
     """Shared machinery of the full models and the headless block stack."""
 
     def _setup(self, specs, pad, V, S, c_in, classes, head, A, path, adaptive=False):
-        self._adaptive = bool(adaptive)
+        default = "adaptive" if adaptive else "plain"
+        specs = [sp if sp.gconv else sp._replace(gconv=default) for sp in specs]
+        for sp in specs:
+            if sp.gconv not in GCONV_KINDS:
+                raise ValueError(f"unknown graph conv kind {sp.gconv!r}")
         self._specs, self._pad, self._V, self._S, self._c_in = list(specs), int(pad), int(V), int(S), int(c_in)
         self._classes, self._head, self._path = int(classes), bool(head), path
         self._engine, self._dirty, self._shape = None, True, None
@@ -269,10 +333,10 @@ class _CoBase(nn.Module):
         cfg.pool_size, cfg.pool_padding = (self.pool_size, self.pool_padding) if self._head else (0, 0)
         cfg.data_bn = 1 if self._head else 0
         cfg.path = {"auto": 0, "simt": 1}[self._path]
-        cfg.graph_conv = 1 if self._adaptive else 0
         for i, sp in enumerate(self._specs):
             cfg.blocks[i].cin, cfg.blocks[i].cout = sp.cin, sp.cout
             cfg.blocks[i].stride, cfg.blocks[i].res_kind = sp.stride, sp.res_kind
+            cfg.blocks[i].gconv = GCONV_KINDS[sp.gconv]
         return cfg
 
     def simulate_schedule(self, frames):
@@ -491,8 +555,8 @@ class CoModelBase(_CoBase):
         self.data_bn = nn.BatchNorm1d(S * c_in * V)
         _init_bn(self.data_bn, 1)
         self.layers = _Node()
-        for i, sp in enumerate(specs):
-            self.layers.add_module(f"layer{i + 1}", _block_params(sp, self.graph.A, self.PADDING, self.ADAPTIVE))
+        for i, sp in enumerate(self._specs):
+            self.layers.add_module(f"layer{i + 1}", _block_params(sp, self.graph.A, self.PADDING, sp.gconv))
         self.fc = nn.Linear(256, classes)
         nn.init.normal_(self.fc.weight, 0, math.sqrt(2.0 / classes))  # models/utils.py:23-24
 
@@ -606,6 +670,18 @@ class CoAGcn(CoModelBase):
     PADDING, STRIDED, ADAPTIVE = 4, True, True
 
 
+class CoSTr(CoModelBase):
+    """CoS-TR: the CoST-GCN geometry with the spatial self-attention unit ``GcnUnitAttention`` as the graph conv of
+    layers 4-10, stepped one frame at a time (models/cos_tr/cos_tr.py:12-47)."""
+
+    PADDING, STRIDED = 4, True
+
+    @classmethod
+    def block_specs(cls, c_in):
+        specs = super().block_specs(c_in)
+        return specs[:3] + [sp._replace(gconv="attention") for sp in specs[3:]]
+
+
 # ---------------------------------------------------------------------------------------------
 # headless stack of blocks (what the reference's block-level tests build with co.Sequential)
 # ---------------------------------------------------------------------------------------------
@@ -619,8 +695,8 @@ class CoStack(_CoBase):
         g = _graph.ntu_graph() if skeleton == "ntu" else _graph.kinetics_graph()
         specs = [b if isinstance(b, BlockSpec) else BlockSpec(*b) for b in blocks]
         self._setup(specs, padding, g.num_node, 1, specs[0].cin, 0, False, g.A, kernel_path, adaptive)
-        for i, sp in enumerate(specs):
-            self.add_module(str(i), _block_params(sp, g.A, padding, adaptive))
+        for i, sp in enumerate(self._specs):
+            self.add_module(str(i), _block_params(sp, g.A, padding, sp.gconv))
         self.eval()
 
     def _block_modules(self):

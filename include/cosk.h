@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 #define COSK_MAX_BLOCKS 16
-#define COSK_ABI_VERSION 2
+#define COSK_ABI_VERSION 3
 
 typedef struct cosk_model cosk_model;
 
@@ -44,17 +44,20 @@ enum cosk_path {
   COSK_PATH_SIMT = 1  /* fp32 CUDA-core kernels everywhere: on-device checker, not the product */
 };
 
-/* graph convolution of every block */
+/* graph convolution of a block */
 enum cosk_graph_conv {
-  COSK_GCONV_PLAIN = 0,   /* GraphConvolution: fixed sparse A * graph_attn (models/base.py:230-270) */
-  COSK_GCONV_ADAPTIVE = 1 /* AdaptiveGraphConvolution: dense A + graph_attn plus a per-frame softmax vertex attention
-                             (models/a_gcn/a_gcn.py:12-69, stepped by models/coa_gcn/coa_gcn.py:11-14) */
+  COSK_GCONV_PLAIN = 0,    /* GraphConvolution: fixed sparse A * graph_attn (models/base.py:230-270) */
+  COSK_GCONV_ADAPTIVE = 1, /* AdaptiveGraphConvolution: dense A + graph_attn plus a per-frame softmax vertex attention
+                              (models/a_gcn/a_gcn.py:12-69, stepped by models/coa_gcn/coa_gcn.py:11-14) */
+  COSK_GCONV_ATTENTION = 2 /* GcnUnitAttention, only_attention: 8-head self-attention over the V vertices of a frame
+                              (models/s_tr/s_tr.py:19-231,303-476; layers 4-10 of models/cos_tr/cos_tr.py:24-41) */
 };
 
 typedef struct {
   int32_t cin, cout;
   int32_t stride;   /* temporal stride of tcn and residual conv: 1 or 2 */
   int32_t res_kind; /* enum cosk_res_kind */
+  int32_t gconv;    /* enum cosk_graph_conv */
 } cosk_block_cfg;
 
 /* Geometry of a stack.  Mirrors what CoStGcn.__init__ / CoStGcnMod.__init__
@@ -73,7 +76,6 @@ typedef struct {
   int32_t data_bn;      /* 1: per-feature affine of data_bn (models/base.py:76) on the input */
   int32_t device;       /* CUDA device ordinal */
   int32_t path;         /* enum cosk_path */
-  int32_t graph_conv;   /* enum cosk_graph_conv */
   cosk_block_cfg blocks[COSK_MAX_BLOCKS];
 } cosk_config;
 
@@ -88,6 +90,13 @@ void cosk_destroy(cosk_model *m);
  *                                              A + graph_attn for COSK_GCONV_ADAPTIVE (models/a_gcn/a_gcn.py:50)
  *   "block<i>.att.w"  "block<i>.att.b"         [6*(cout/4)][cin], [6*(cout/4)]   COSK_GCONV_ADAPTIVE only: the embedding
  *                                              convs, rows theta_0, phi_0, theta_1, phi_1, theta_2, phi_2 (a_gcn.py:53-60)
+ *   COSK_GCONV_ATTENTION blocks take, instead of mix / gcn.w as above:
+ *   "block<i>.sa.in_scale" "block<i>.sa.in_shift"  [cin*V]  the unit's data_bn, feature c*V + v (s_tr.py:424-427)
+ *   "block<i>.sa.qkv.w"  "block<i>.sa.qkv.b"   [2*dk + dv][cin], [2*dk + dv]  dk = cout/4, dv = cout, rows q | k | v with the
+ *                                              dkh^-0.5 query scale folded in (s_tr.py:233-252)
+ *   "block<i>.gcn.w"  "block<i>.gcn.b"         [cout][cout], [cout]  the output conv (s_tr.py:229-230) with the unit's bn folded
+ *   "block<i>.sa.skip_scale"                   [cout]  scale of that bn: the skip connection x (cin == cout) is added before
+ *                                              the bn (s_tr.py:464-470), i.e. enters as skip_scale[c] * x[c]
  *   "block<i>.gcn.w"                           [cout][3*cin (+cin if cin != cout)]  partition-major K
  *   "block<i>.gcn.b"                           [cout]
  *   "block<i>.tcn.w"                           [cout][9*cout]  tap-major K (tap 8 = newest frame)
@@ -132,7 +141,8 @@ int64_t cosk_frame_count(const cosk_model *m);
 int cosk_read_block(cosk_model *m, int32_t block, float *dst_dev, void *stream);
 /* kernels launched by this handle since creation */
 int64_t cosk_launch_count(const cosk_model *m);
-/* 1 iff block i runs on the tcgen05 kernels (bit 0: graph conv, bit 1: temporal conv) */
+/* 1 iff block i runs on the tcgen05 kernels (bit 0: graph conv -- for a COSK_GCONV_ATTENTION block the unit's output
+ * conv; its qkv conv and the attention itself run on CUDA cores --, bit 1: temporal conv) */
 int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block);
 
 /* Per-kernel-kind device timing with CUDA events on the launching stream.

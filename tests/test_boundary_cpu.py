@@ -32,13 +32,16 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header():
-    # 13 int32 fields + 16 blocks of 4 int32
-    assert ctypes.sizeof(cslib.Config) == 4 * (13 + 4 * cslib.MAX_BLOCKS)
+    # 12 int32 fields + 16 blocks of 5 int32
+    assert ctypes.sizeof(cslib.Config) == 4 * (12 + 5 * cslib.MAX_BLOCKS)
     header = open(os.path.join(ROOT, "include", "cosk.h")).read()
     body = header[header.index("typedef struct {\n  int32_t abi_version"): header.index("} cosk_config;")]
     fields = re.findall(r"int32_t\s+(\w+);", body)
     assert fields == [n for n, _ in cslib.Config._fields_[:-1]]
     assert int(re.search(r"#define COSK_ABI_VERSION (\d+)", header).group(1)) == cslib.ABI_VERSION
+    blk = header[header.index("typedef struct {\n  int32_t cin, cout;"): header.index("} cosk_block_cfg;")]
+    assert re.findall(r"int32_t\s+([\w, ]+);", blk) == ["cin, cout", "stride", "res_kind", "gconv"]
+    assert [n for n, _ in cslib.BlockCfg._fields_] == ["cin", "cout", "stride", "res_kind", "gconv"]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -222,7 +225,8 @@ def test_coa_gcn_host_model():
     the folded tensors of the adaptive layout, and NTU-120 class count (BASELINE configs[2])."""
     torch.manual_seed(0)
     m = cs.CoAGcn({"dataset_name": "ntu120"})
-    assert m.num_classes == 120 and m._config().graph_conv == 1 and cs.CoStGcn()._config().graph_conv == 0
+    assert m.num_classes == 120
+    assert [m._config().blocks[i].gconv for i in range(10)] == [1] * 10 and cs.CoStGcn()._config().blocks[3].gconv == 0
     sd = m.state_dict()
     assert sd["layers.layer1.gcn.a_conv.0.weight"].shape == (16, 3, 1, 1)
     assert sd["layers.layer10.0.1.gcn.b_conv.2.weight"].shape == (64, 256, 1, 1)
@@ -240,3 +244,35 @@ def test_coa_gcn_host_model():
     assert torch.equal(t["att.w"][64:96], gcn.a_conv[1].weight.detach()[:, :, 0, 0])
     with pytest.raises(ValueError):
         cs.CoStack([cs.BlockSpec(2, 2, 1, True)], adaptive=True)  # out_channels // 4 == 0, as in the reference
+
+
+def test_cos_tr_host_model(golden):
+    """CoSTr: the reference's key names for the attention unit (models/s_tr/s_tr.py:352-415 under the block wrappers),
+    strict loading of a regular S-TR state_dict, and the folded tensors reproducing the oracle's unit (host logic)."""
+    m = cs.CoSTr({"dataset_name": "dummy_kin"})
+    assert m.num_classes == 400 and m._V == 18
+    assert [m._config().blocks[i].gconv for i in range(10)] == [0, 0, 0] + [2] * 7
+    own = list(m.state_dict().keys())
+    assert "layers.layer4.0.1.gcn.attention_conv.qkv_conv.weight" in own
+    assert "layers.layer5.0.1.gcn.data_bn.running_mean" in own and "layers.layer3.0.1.gcn.g_conv.2.bias" in own
+    arch = weights.cos_tr_arch()
+    sd = weights.make_state_dict(arch, seed=8, randomize=True)
+    res = m.load_state_dict(m.map_state_dict(sd), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    from continual_skeletons_b200 import model as _m
+
+    blk, spec = m.layers.layer6, m._specs[5]
+    t = _m._folded_block_tensors(blk, spec)
+    assert t["sa.qkv.w"].shape == (2 * 32 + 128, 128) and t["sa.in_scale"].shape == (128 * 18,) and t["gcn.w"].shape == (128, 128)
+    # apply the folded tensors with plain torch ops and compare with the oracle's unit on two frames
+    x = weights.make_input((3, 128, 2, 18), seed=5)
+    want = regular.graph_conv(x, sd, "layers.layer6.gcn.")
+    xn = x * t["sa.in_scale"].view(1, 128, 1, 18) + t["sa.in_shift"].view(1, 128, 1, 18)
+    qkv = torch.einsum("oc,bctv->botv", t["sa.qkv.w"], xn) + t["sa.qkv.b"].view(1, -1, 1, 1)
+    q, k, v = qkv[:, :32], qkv[:, 32:64], qkv[:, 64:]
+    B, T, V = 3, 2, 18
+    q, k, v = (z.reshape(B, 8, -1, T, V) for z in (q, k, v))
+    w = torch.softmax(torch.einsum("bhdti,bhdtj->bhtij", q, k), dim=-1)
+    o = torch.einsum("bhtij,bhdtj->bhdti", w, v).reshape(B, 128, T, V)
+    got = torch.relu(torch.einsum("oc,bctv->botv", t["gcn.w"], o) + t["gcn.b"].view(1, -1, 1, 1) + t["sa.skip_scale"].view(1, -1, 1, 1) * x)
+    assert torch.allclose(got, want, atol=2e-5 * max(1.0, float(want.abs().max())))

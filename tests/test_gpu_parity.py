@@ -14,7 +14,7 @@ import torch
 
 import continual_skeletons_b200 as cs
 from oracle import regular, step, weights
-from oracle.make_golden import ADAPTIVE_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
+from oracle.make_golden import ADAPTIVE_BLOCK_CASES, ATTENTION_BLOCK_CASES, BLOCK_B, BLOCK_CASES, BLOCK_T
 from oracle.weights import ArchSpec
 
 pytestmark = pytest.mark.gpu
@@ -433,3 +433,85 @@ def test_full_size_4096_streams_replica_property(golden, cls, arch_fn, tag):
     assert m.device_error() == 0
     assert tuple(big.shape) == (2 * reps, 60)
     assert torch.equal(big.view(reps, 2, 60), small.unsqueeze(0).expand(reps, 2, 60))
+
+
+# ---------------------------------------------------------------------------------------------
+# CoS-TR: spatial self-attention unit
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("rnd", [False, True])
+@pytest.mark.parametrize("idx", range(len(ATTENTION_BLOCK_CASES)))
+def test_attention_block_step_vs_golden(golden, idx, rnd, path):
+    """Block with GcnUnitAttention stepped frame by frame == the reference's block on the NTU / Kinetics graphs."""
+    name, cin, cout, stride, residual, pad, skel = ATTENTION_BLOCK_CASES[idx]
+    arch = ArchSpec([weights.BlockSpec(cin, cout, stride, residual, gconv="attention")], padding=pad, head=False, block_names=[""], skeleton=skel)
+    sd = weights.make_state_dict(arch, seed=5000 + idx, randomize=rnd)
+    wide = "wide" in name
+    x = weights.make_input((1 if wide else BLOCK_B, cin, 14 if wide else BLOCK_T, arch.vertices), seed=6000 + idx)
+    spec = cs.BlockSpec(cin, cout, stride, residual, "attention")
+    stack = cs.CoStack([spec], padding=pad, skeleton=skel, kernel_path=path)
+    stack.load_state_dict(_stack_keys(sd, spec), strict=True)
+    target = torch.from_numpy(golden["cos_blocks"][name + ("_rnd" if rnd else "")])
+    xd = x.to(DEV)
+    emitted = []
+    for t in range(x.shape[2]):
+        o = stack.forward_step(xd[:, :, t].contiguous())
+        due = t >= 8 - pad and (t - (8 - pad)) % stride == 0
+        assert (o is not None) == due, (name, t)
+        if o is not None:
+            emitted.append(o.cpu())
+    assert stack.device_error() == 0, hex(stack.device_error())
+    assert len(emitted) == (x.shape[2] - (8 - pad) + stride - 1) // stride
+    for j, o in enumerate(emitted):
+        assert _rel_err(o, target[:, :, j]) < BLOCK_RTOL, (name, rnd, path, j, _rel_err(o, target[:, :, j]))
+    if path == "auto" and wide:
+        assert stack.tensor_core_blocks() == [3]
+
+
+def _load_cos_tr(rnd, path="auto"):
+    arch = weights.cos_tr_arch()
+    sd = weights.make_state_dict(arch, seed=8 if rnd else 7, randomize=rnd)
+    m = cs.CoSTr({"dataset_name": "dummy_kin", "kernel_path": path})
+    m.load_state_dict(m.map_state_dict(sd), strict=True)
+    return arch, sd, m
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("rnd", [False, True])
+def test_cos_tr_forward_steps_vs_reference(golden, rnd, path):
+    """CoSTr.forward_steps over (2, 3, 300, 18, 2) (Kinetics skeleton, 400 classes): logits as the reference blocks give."""
+    arch, sd, m = _load_cos_tr(rnd, path)
+    x = weights.make_input((2, 3, 300, 18, 2), seed=11)
+    out = m.forward_steps(x.to(DEV))
+    assert m.device_error() == 0, hex(m.device_error())
+    assert out is not None and tuple(out.shape) == (2, 400)
+    out = out.cpu()
+    want = torch.from_numpy(golden["cos_tr"]["cos_tr_co_logits" + ("_rnd" if rnd else "")])
+    scale = max(1.0, float(want.abs().max()) / 16.0)
+    err = float((out - want).abs().max())
+    assert err <= 1e-3 * scale, (rnd, path, err, float(want.abs().max()))
+    assert torch.equal(out.argmax(1), want.argmax(1))
+    if path == "auto":
+        assert m.tensor_core_blocks() == [2] + [3] * 9
+
+
+def test_cos_tr_schedule_and_replicas():
+    """Per-frame emission flags bit-exact against the step oracle; replicated streams give bit-identical logits."""
+    arch, sd, m = _load_cos_tr(True)
+    T = 40
+    x = weights.make_input((2, 3, T, 18, 2), seed=12)
+    ref = step.StepModel(sd, arch)
+    xd = x.to(DEV)
+    for t in range(T):
+        with torch.no_grad():
+            want = ref.forward_step(x[:, :, t])
+        got = m.forward_step(xd[:, :, t].contiguous())
+        assert m.last_schedule() == ref.trace[-1], t
+        assert (got is None) == (want is None)
+    base = weights.make_input((2, 3, 300, 18, 2), seed=11).to(DEV)
+    m.clean_state()  # forward_steps continues from the current state (models/base.py:187-190)
+    small = m.forward_steps(base)
+    reps = 75  # 150 streams x 2 persons = 300 skeletons: not a multiple of the 7 skeletons per tile
+    big = m.forward_steps(base.repeat(reps, 1, 1, 1, 1))
+    assert m.device_error() == 0
+    assert torch.equal(big.view(reps, 2, 400), small.unsqueeze(0).expand(reps, 2, 400))
