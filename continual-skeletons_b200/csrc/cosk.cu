@@ -53,6 +53,17 @@ struct BlockW {
   CUtensorMap map_sa_w, map_sa_w_half;
   bool tc_sa_out = false, sa_res_kblock = false;
   ActBuf sa;  // attention output rows of the frame in flight (1 slot), operand of the output conv
+  // tensor-core qkv conv: normalised input rows, q | k | v rows (zero-padded to nq_pad columns), and the conv split into
+  // column chunks of a width the single-tap temporal-conv kernel is instantiated for
+  bool tc_sa_qkv = false;
+  ActBuf sa_x, sa_q;
+  int nq_pad = 0, n_qchunks = 0;
+  struct QChunk {
+    int width = 0, col0 = 0;
+    __nv_bfloat16 *w16 = nullptr;
+    float *bias = nullptr;
+    CUtensorMap map, map_half;
+  } qchunk[2];
   int mix_max_nz = 0;
   int gcn_parts = 4;  // accumulator column groups of the tensor-core graph conv (3 or 4)
   int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
@@ -90,6 +101,7 @@ struct cosk_model {
   int merge_min_tiles = 4 * 148;  // below this the two CTA groups are not worth splitting (COSK_MERGE_MIN_TILES)
   int merge_split64 = 100;  // CTAs given to the temporal-conv role (64-channel layers)
   int merge_split128 = 92;  // same for the 128-channel layers (CTA pairs)
+  int sa_qkv_tc = 1;  // qkv conv of the self-attention unit on the tcgen05 single-tap kernel (COSK_SA_QKV_TC=0: fp32 CUDA-core GEMM)
   int attn_tc = 1;  // attention half of the adaptive graph conv on tcgen05 (COSK_ATTN_TC=0: fp32 CUDA-core kernel)
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
@@ -155,6 +167,8 @@ void free_state(cosk_model *m) {
     dfree(b.out.ptr);
     dfree(b.d_tile_cnt);
     dfree(b.sa.ptr);
+    dfree(b.sa_x.ptr);
+    dfree(b.sa_q.ptr);
   }
   dfree(m->d_qkv);
   dfree(m->d_pool_ring);
@@ -373,6 +387,31 @@ int prepare(cosk_model *m) {
       if ((rc = upload(m, b.d_sa_qkv_b, b.sa_qkv_b.data(), b.sa_qkv_b.size()))) return rc;
       if ((rc = upload(m, b.d_sa_scale, b.sa_scale.data(), b.sa_scale.size()))) return rc;
       if ((rc = upload(m, b.d_sa_shift, b.sa_shift.data(), b.sa_shift.size()))) return rc;
+      b.tc_sa_qkv = want_tc && m->sa_qkv_tc && bc.cin % kBK == 0 && tc_width(bc.cout);
+      if (b.tc_sa_qkv) {
+        const int nq = 2 * (bc.cout / 4) + bc.cout;
+        b.n_qchunks = bc.cout == 256 ? 2 : 1;
+        b.qchunk[0].width = bc.cout == 64 ? 128 : 256;
+        b.qchunk[0].col0 = 0;
+        b.qchunk[1].width = 128;
+        b.qchunk[1].col0 = 256;
+        b.nq_pad = bc.cout == 64 ? 128 : bc.cout == 128 ? 256 : 384;
+        for (int q = 0; q < b.n_qchunks; ++q) {
+          BlockW::QChunk &qc = b.qchunk[q];
+          std::vector<float> w((size_t)qc.width * bc.cin, 0.f), bb((size_t)qc.width, 0.f);
+          for (int r = 0; r < qc.width; ++r) {
+            const int src = qc.col0 + r;
+            if (src >= nq) continue;  // zero padding
+            memcpy(&w[(size_t)r * bc.cin], &b.sa_qkv_w[(size_t)src * bc.cin], sizeof(float) * bc.cin);
+            bb[r] = b.sa_qkv_b[src];
+          }
+          std::vector<uint16_t> s16 = split_rows(w, qc.width, bc.cin);
+          if ((rc = upload(m, reinterpret_cast<uint16_t *&>(qc.w16), s16.data(), s16.size()))) return rc;
+          if ((rc = upload(m, qc.bias, bb.data(), bb.size()))) return rc;
+          if ((rc = make_map(m, &qc.map, qc.w16, (uint64_t)bc.cin, (uint64_t)2 * qc.width, (uint32_t)qc.width))) return rc;
+          if ((rc = make_map(m, &qc.map_half, qc.w16, (uint64_t)bc.cin, (uint64_t)2 * qc.width, (uint32_t)qc.width / 2))) return rc;
+        }
+      }
       // The skip connection is added before the unit's bn, so it enters scaled per channel: a diagonal "residual conv".
       if (!res_conv) {
         std::vector<float> diag((size_t)bc.cin * bc.cout, 0.f);  // k-major [cin][cout]
@@ -675,6 +714,21 @@ int run_tcn_gcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long 
   return COSK_OK;
 }
 
+// The temporal-conv kernel as a plain token-major GEMM of output width `width` (64 / 128 / 256), on CTA pairs where the
+// temporal convs of that width use them; `half` is the weight map with half-height boxes the 256-wide pair kernel wants.
+int launch_onetap(cosk_model *m, int width, TcTcnArgs &a, const CUtensorMap &half, cudaStream_t s) {
+  const bool pair = m->n_tiles >= 2 && (m->pair_mask & (width == 64 ? 1 : width == 128 ? 2 : 4));
+  if (pair) {
+    if (width > 128) a.tm_w = half;
+    if (width == 64) return launch_tc_tcn2<64>(m, a, s);
+    if (width == 128) return launch_tc_tcn2<128>(m, a, s);
+    return launch_tc_tcn2<256>(m, a, s);
+  }
+  if (width == 64) return launch_tc_tcn<64>(m, a, s);
+  if (width == 128) return launch_tc_tcn<128>(m, a, s);
+  return launch_tc_tcn<256>(m, a, s);
+}
+
 // Self-attention unit of CoS-TR (GcnUnitAttention, only_attention): qkv conv on the data_bn-normalised frame, 8-head
 // attention over the vertices of each skeleton, then the output conv + bn + skip + ReLU -- the last one is the
 // temporal-conv kernel run with a single tap on the attention rows.
@@ -683,7 +737,54 @@ int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int 
   BlockW &b = m->blk[i];
   const int dk = bc.cout / 4, dv = bc.cout, nq = 2 * dk + dv;
   int rc;
-  {
+  if (b.tc_sa_qkv) {
+    {  // data_bn of the unit as a pre-pass: the GEMM operand must exist in memory for TMA
+      SaAffineArgs a;
+      a.x_hi = in.hi(in_slot);
+      a.x_lo = in.lo(in_slot);
+      a.y_hi = b.sa_x.hi(0);
+      a.y_lo = b.sa_x.lo(0);
+      a.cs = in.cs;
+      a.c = bc.cin;
+      a.V = m->cfg.vertices;
+      a.scale = b.d_sa_scale;
+      a.shift = b.d_sa_shift;
+      a.n_tokens = m->n_tokens;
+      const long long n = m->n_tokens * (bc.cin / 8);
+      CK(launch_k(m, k_sa_affine, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a));
+      m->launches++;
+    }
+    for (int q = 0; q < b.n_qchunks; ++q) {  // qkv conv = single-tap temporal-conv kernel without ReLU, per column chunk
+      const BlockW::QChunk &qc = b.qchunk[q];
+      TcTcnArgs a;
+      a.tm_ring = b.sa_x.map;
+      a.tm_res = b.sa_x.map;
+      a.tm_w = qc.map;
+      for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.sa_x.row_hi(0);
+      a.res_row = 0;
+      a.t_alloc = (int)m->t_alloc;
+      a.n_taps = 1;
+      a.kb_per_tap = bc.cin / kBK;
+      a.kb_res = 0;
+      a.n_tiles = m->n_tiles;
+      a.tile_tokens = m->tile_tokens;
+      a.reverse = 0;
+      a.n_tokens = m->n_tokens;
+      a.epi.bias = qc.bias;
+      a.epi.r_hi = nullptr;
+      a.epi.r_lo = nullptr;
+      a.epi.cs_r = 0;
+      a.epi.y_hi = b.sa_q.hi(0) + qc.col0;
+      a.epi.y_lo = b.sa_q.lo(0) + qc.col0;
+      a.epi.cs_out = b.sa_q.cs;
+      a.epi.floor = -INFINITY;
+      a.tile_cnt = nullptr;
+      a.trace = nullptr;
+      a.dbg = m->d_dbg;
+      if ((rc = launch_onetap(m, qc.width, a, qc.map_half, s))) return rc;
+      m->launches++;
+    }
+  } else {
     SaQkvArgs a;
     a.x_hi = in.hi(in_slot);
     a.x_lo = in.lo(in_slot);
@@ -705,16 +806,22 @@ int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int 
   {
     SaAttnArgs a;
     a.qkv = m->d_qkv;
+    a.q_hi = b.tc_sa_qkv ? b.sa_q.hi(0) : nullptr;
+    a.q_lo = b.tc_sa_qkv ? b.sa_q.lo(0) : nullptr;
+    a.cs_q = b.sa_q.cs;
     a.dk = dk;
     a.dv = dv;
-    a.heads = 8;  // Nh of GcnUnitAttention, never overridden by the reference (models/s_tr/s_tr.py:311)
     a.V = m->cfg.vertices;
     a.n_tokens = m->n_tokens;
     a.tile_tokens = m->tile_tokens;
     a.y_hi = b.sa.hi(0);
     a.y_lo = b.sa.lo(0);
     a.cs_out = b.sa.cs;
-    CK(launch_k(m, k_sa_attn, dim3(m->n_tiles), dim3(128), 0, s, a));
+    const int dvh = dv / kSaHeads;
+    if (dvh == 8) CK(launch_k(m, k_sa_attn<8>, dim3(m->n_tiles), dim3(256), 0, s, a));
+    else if (dvh == 16) CK(launch_k(m, k_sa_attn<16>, dim3(m->n_tiles), dim3(256), 0, s, a));
+    else if (dvh == 32) CK(launch_k(m, k_sa_attn<32>, dim3(m->n_tiles), dim3(256), 0, s, a));
+    else CK(launch_k(m, k_sa_attn_any, dim3(m->n_tiles), dim3(128), 0, s, a));
     m->launches++;
   }
   if ((rc = prof_mark(m, 1, i, s))) return rc;
@@ -744,18 +851,7 @@ int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int 
     a.tile_cnt = nullptr;
     a.trace = nullptr;
     a.dbg = m->d_dbg;
-    const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
-    if (pair) {
-      if (bc.cout > 128) a.tm_w = b.map_sa_w_half;
-      if (bc.cout == 64) rc = launch_tc_tcn2<64>(m, a, s);
-      else if (bc.cout == 128) rc = launch_tc_tcn2<128>(m, a, s);
-      else rc = launch_tc_tcn2<256>(m, a, s);
-    } else {
-      if (bc.cout == 64) rc = launch_tc_tcn<64>(m, a, s);
-      else if (bc.cout == 128) rc = launch_tc_tcn<128>(m, a, s);
-      else rc = launch_tc_tcn<256>(m, a, s);
-    }
-    if (rc) return rc;
+    if ((rc = launch_onetap(m, bc.cout, a, b.map_sa_w_half, s))) return rc;
   } else {
     TcnArgs a;
     for (int k = 0; k < kTaps; ++k) {
@@ -1100,6 +1196,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
   if (const char *e = getenv("COSK_ATTN_TC")) m->attn_tc = atoi(e);
+  if (const char *e = getenv("COSK_SA_QKV_TC")) m->sa_qkv_tc = atoi(e);
   if (const char *e = getenv("COSK_TCN_IDENTITY_MMA")) m->tcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_MERGE")) m->merge = atoi(e);
   if (const char *e = getenv("COSK_MERGE_MIN_TILES")) m->merge_min_tiles = atoi(e);
@@ -1165,6 +1262,10 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_sa_qkv_b);
     dfree(b.d_sa_w16);
     dfree(b.d_res_w_sa);
+    for (auto &qc : b.qchunk) {
+      dfree(qc.w16);
+      dfree(qc.bias);
+    }
   }
   dfree(m->d_bn_scale);
   dfree(m->d_bn_shift);
@@ -1252,6 +1353,12 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
       max_nq = std::max(max_nq, 2 * (c.blocks[i].cout / 4) + c.blocks[i].cout);
       if ((rc = alloc_act(m, m->blk[i].sa, 1, c.blocks[i].cout))) return rc;
       CK(cudaMemset(m->blk[i].sa.ptr, 0, m->blk[i].sa.bytes()));
+      if (m->blk[i].tc_sa_qkv) {
+        if ((rc = alloc_act(m, m->blk[i].sa_x, 1, c.blocks[i].cin))) return rc;
+        if ((rc = alloc_act(m, m->blk[i].sa_q, 1, m->blk[i].nq_pad))) return rc;
+        CK(cudaMemset(m->blk[i].sa_x.ptr, 0, m->blk[i].sa_x.bytes()));
+        CK(cudaMemset(m->blk[i].sa_q.ptr, 0, m->blk[i].sa_q.bytes()));
+      }
     }
   }
   if (max_nq) {

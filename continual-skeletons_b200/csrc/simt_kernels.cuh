@@ -434,20 +434,189 @@ __global__ void __launch_bounds__(256) k_sa_qkv(SaQkvArgs a) {
   }
 }
 
+// data_bn of the attention unit as a pre-pass (tensor-core path): x'[c] = x[c] * scale[c][v] + shift[c][v] on the
+// split-bf16 rows, 8 channels per thread
+struct SaAffineArgs {
+  const __nv_bfloat16 *x_hi, *x_lo;
+  __nv_bfloat16 *y_hi, *y_lo;
+  int cs, c, V;  // same row stride in and out
+  const float *scale, *shift;
+  long long n_tokens;
+};
+
+__global__ void __launch_bounds__(256) k_sa_affine(SaAffineArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int per_row = a.c / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.n_tokens * per_row) return;
+  const long long tok = idx / per_row;
+  const int c0 = (int)(idx - tok * per_row) * 8;
+  const int wv = (int)(tok % a.V);
+  const uint4 h = *reinterpret_cast<const uint4 *>(a.x_hi + tok * a.cs + c0);
+  const uint4 l = *reinterpret_cast<const uint4 *>(a.x_lo + tok * a.cs + c0);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  uint32_t oh[4], ol[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const int c = c0 + 2 * w;
+    const float x0 = (bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w])) * a.scale[c * a.V + wv] + a.shift[c * a.V + wv];
+    const float x1 = (bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w])) * a.scale[(c + 1) * a.V + wv] + a.shift[(c + 1) * a.V + wv];
+    oh[w] = pack_bf16x2(x0, x1);
+    ol[w] = pack_bf16x2(x0 - bf16_lo_as_float(oh[w]), x1 - bf16_hi_as_float(oh[w]));
+  }
+  *reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs + c0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+  *reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs + c0) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+}
+
 struct SaAttnArgs {
-  const float *qkv;  // [token][2*dk + dv]
-  int dk, dv, heads, V;
+  const float *qkv;                  // fp32 rows [token][nq] (CUDA-core qkv conv) ...
+  const __nv_bfloat16 *q_hi, *q_lo;  // ... or split-bf16 rows [token][cs_q] (tensor-core qkv conv); nullptr selects fp32
+  int cs_q;
+  int dk, dv, V;  // 8 heads: dkh = dk/8, dvh = dv/8
   long long n_tokens;
   int tile_tokens;
   __nv_bfloat16 *y_hi, *y_lo;  // [token][cs_out]
   int cs_out;
 };
 
+constexpr int kSaHeads = 8;    // Nh of GcnUnitAttention, never overridden by the reference (models/s_tr/s_tr.py:311)
 constexpr int kSaMaxDkh = 8;   // dk / heads of a 256-channel unit
 constexpr int kSaMaxDvh = 32;  // dv / heads
 
-// one token tile per CTA, thread = token row; k and v of the current head staged in shared memory
-__global__ void __launch_bounds__(128) k_sa_attn(SaAttnArgs a) {
+// N consecutive columns of a token's q | k | v row as fp32: 16-byte loads of the hi and lo planes where N allows,
+// fp32 loads when the row comes from the CUDA-core qkv conv
+template <int N>
+__device__ __forceinline__ void sa_load_cols(const SaAttnArgs &a, long long tok, int col, float (&out)[N]) {
+  if (a.q_hi == nullptr) {
+    const float *p = a.qkv + tok * (2 * a.dk + a.dv) + col;
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = p[i];
+    return;
+  }
+  const __nv_bfloat16 *ph = a.q_hi + tok * a.cs_q + col, *pl = a.q_lo + tok * a.cs_q + col;
+  if (N % 8 == 0) {
+#pragma unroll
+    for (int g = 0; g < N / 8; ++g) {
+      const uint4 h = *reinterpret_cast<const uint4 *>(ph + 8 * g), l = *reinterpret_cast<const uint4 *>(pl + 8 * g);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        out[8 * g + 2 * w] = bf16_lo_as_float(hw[w]) + bf16_lo_as_float(lw[w]);
+        out[8 * g + 2 * w + 1] = bf16_hi_as_float(hw[w]) + bf16_hi_as_float(lw[w]);
+      }
+    }
+  } else {  // 2 or 4 columns: 4-byte loads
+#pragma unroll
+    for (int w = 0; w < N / 2; ++w) {
+      const uint32_t h = *reinterpret_cast<const uint32_t *>(ph + 2 * w), l = *reinterpret_cast<const uint32_t *>(pl + 2 * w);
+      out[2 * w] = bf16_lo_as_float(h) + bf16_lo_as_float(l);
+      out[2 * w + 1] = bf16_hi_as_float(h) + bf16_hi_as_float(l);
+    }
+  }
+}
+
+// One token tile per CTA, 256 threads = 2 heads x 128 token rows; per head: k and v of the tile staged in shared
+// memory as fp32 (each element converted once), then for row i:  w_j = softmax_j <q_i, k_j> over the V vertices of its
+// skeleton and out_i = sum_j w_j v_j, from registers and 16-byte broadcast loads; the dvh outputs leave as packed
+// split-bf16 rows.  DVH = dv / 8, dkh = DVH / 4.
+template <int DVH>
+__global__ void __launch_bounds__(256) k_sa_attn(SaAttnArgs a) {
+  constexpr int DKH = DVH / 4;
+  constexpr int KP = DKH < 4 ? 4 : DKH;  // padded to whole float4s
+  __shared__ __align__(16) float ks[2][kTileRows][KP];
+  __shared__ __align__(16) float vs[2][kTileRows][DVH + 4];
+  pdl_trigger();
+  pdl_wait();
+  const int row = threadIdx.x & 127, hh = threadIdx.x >> 7;
+  const long long tok0 = (long long)blockIdx.x * a.tile_tokens;
+  long long remain = a.n_tokens - tok0;
+  const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
+  const bool valid = row < rows_valid;
+  const long long tok = tok0 + row;
+  const int sk0 = valid ? row - row % a.V : 0;
+  for (int h = hh; h < kSaHeads; h += 2) {
+    __syncthreads();
+    if (valid) {
+      float kk[DKH], vv[DVH];
+      sa_load_cols<DKH>(a, tok, a.dk + h * DKH, kk);
+      sa_load_cols<DVH>(a, tok, 2 * a.dk + h * DVH, vv);
+#pragma unroll
+      for (int d = 0; d < KP; ++d) ks[hh][row][d] = d < DKH ? kk[d] : 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < DVH / 4; ++d4)
+        *reinterpret_cast<float4 *>(&vs[hh][row][4 * d4]) = make_float4(vv[4 * d4], vv[4 * d4 + 1], vv[4 * d4 + 2], vv[4 * d4 + 3]);
+    }
+    __syncthreads();
+    if (!valid) continue;
+    float q[KP];
+    {
+      float qq[DKH];
+      sa_load_cols<DKH>(a, tok, h * DKH, qq);
+#pragma unroll
+      for (int d = 0; d < KP; ++d) q[d] = d < DKH ? qq[d] : 0.f;
+    }
+    float w[kAttnMaxV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxV; ++j) {
+      if (j < a.V) {
+        float sdot = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < KP / 4; ++d4) {
+          const float4 k4 = *reinterpret_cast<const float4 *>(&ks[hh][sk0 + j][4 * d4]);
+          sdot = fmaf(q[4 * d4], k4.x, sdot);
+          sdot = fmaf(q[4 * d4 + 1], k4.y, sdot);
+          sdot = fmaf(q[4 * d4 + 2], k4.z, sdot);
+          sdot = fmaf(q[4 * d4 + 3], k4.w, sdot);
+        }
+        w[j] = sdot;
+        mx = fmaxf(mx, sdot);
+      } else {
+        w[j] = 0.f;
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxV; ++j)
+      if (j < a.V) {
+        w[j] = expf(w[j] - mx);
+        sum += w[j];
+      }
+    const float inv = 1.0f / sum;
+    float o[DVH];
+#pragma unroll
+    for (int d = 0; d < DVH; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAttnMaxV; ++j)
+      if (j < a.V) {
+        const float wj = w[j] * inv;
+#pragma unroll
+        for (int d4 = 0; d4 < DVH / 4; ++d4) {
+          const float4 v4 = *reinterpret_cast<const float4 *>(&vs[hh][sk0 + j][4 * d4]);
+          o[4 * d4] = fmaf(wj, v4.x, o[4 * d4]);
+          o[4 * d4 + 1] = fmaf(wj, v4.y, o[4 * d4 + 1]);
+          o[4 * d4 + 2] = fmaf(wj, v4.z, o[4 * d4 + 2]);
+          o[4 * d4 + 3] = fmaf(wj, v4.w, o[4 * d4 + 3]);
+        }
+      }
+#pragma unroll
+    for (int g = 0; g < DVH / 8; ++g) {
+      uint32_t oh[4], ol[4];
+#pragma unroll
+      for (int w2 = 0; w2 < 4; ++w2) {
+        const float x0 = o[8 * g + 2 * w2], x1 = o[8 * g + 2 * w2 + 1];
+        oh[w2] = pack_bf16x2(x0, x1);
+        ol[w2] = pack_bf16x2(x0 - bf16_lo_as_float(oh[w2]), x1 - bf16_hi_as_float(oh[w2]));
+      }
+      *reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + h * DVH + 8 * g) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      *reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + h * DVH + 8 * g) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    }
+  }
+}
+
+// any head width (the reference's small test blocks): scalar version of the above
+__global__ void __launch_bounds__(128) k_sa_attn_any(SaAttnArgs a) {
   __shared__ float ks[kTileRows][kSaMaxDkh + 1];
   __shared__ float vs[kTileRows][kSaMaxDvh + 1];
   pdl_trigger();
@@ -457,10 +626,10 @@ __global__ void __launch_bounds__(128) k_sa_attn(SaAttnArgs a) {
   long long remain = a.n_tokens - tok0;
   const int rows_valid = (int)(remain < a.tile_tokens ? remain : a.tile_tokens);
   const bool valid = row < rows_valid;
-  const int nq = 2 * a.dk + a.dv, dkh = a.dk / a.heads, dvh = a.dv / a.heads;
+  const int nq = 2 * a.dk + a.dv, dkh = a.dk / kSaHeads, dvh = a.dv / kSaHeads;
   const int sk0 = valid ? row - row % a.V : 0;
   const float *mine = a.qkv + (tok0 + row) * nq;
-  for (int h = 0; h < a.heads; ++h) {
+  for (int h = 0; h < kSaHeads; ++h) {
     __syncthreads();
     if (valid) {
       for (int d = 0; d < dkh; ++d) ks[row][d] = mine[a.dk + h * dkh + d];
@@ -474,12 +643,12 @@ __global__ void __launch_bounds__(128) k_sa_attn(SaAttnArgs a) {
     float w[kAttnMaxV];
     float mx = -INFINITY;
     for (int j = 0; j < a.V; ++j) {
-      float s = 0.f;
+      float sdot = 0.f;
 #pragma unroll
       for (int d = 0; d < kSaMaxDkh; ++d)
-        if (d < dkh) s = fmaf(q[d], ks[sk0 + j][d], s);
-      w[j] = s;
-      mx = fmaxf(mx, s);
+        if (d < dkh) sdot = fmaf(q[d], ks[sk0 + j][d], sdot);
+      w[j] = sdot;
+      mx = fmaxf(mx, sdot);
     }
     float sum = 0.f;
     for (int j = 0; j < a.V; ++j) {

@@ -84,6 +84,7 @@ struct EpiArgs {
   int cs_r;
   __nv_bfloat16 *y_hi, *y_lo;
   int cs_out;
+  float floor = 0.f;  // lower clamp of the output: 0 = ReLU; -inf when the kernel serves as a plain GEMM (qkv conv)
 };
 
 // One epilogue warp: 32 accumulator rows, COUT fp32 columns each -> bias, residual, ReLU, split,
@@ -125,7 +126,7 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr_row0, const float *
       uint32_t oh[16], ol[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float x0 = fmaxf(v[2 * j], 0.f), x1 = fmaxf(v[2 * j + 1], 0.f);
+        const float x0 = fmaxf(v[2 * j], e.floor), x1 = fmaxf(v[2 * j + 1], e.floor);
         const uint32_t h = pack_bf16x2(x0, x1);
         oh[j] = h;
         ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
