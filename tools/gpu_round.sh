@@ -9,6 +9,7 @@ run smoke 600 python __graft_entry__.py smoke
 run bench_auto 900 python bench.py --steps 200 --warmup 8
 run bench_auto_mod 900 python bench.py --workload cost_gcn_mod --steps 100 --warmup 8 --no-cpu-baseline
 run bench_coa 900 python bench.py --workload coa_gcn --steps 100 --warmup 8 --no-cpu-baseline
+run bench_cos 900 python bench.py --workload cos_tr --streams 2048 --steps 100 --warmup 8 --no-cpu-baseline
 run bench_script 600 python scripts/benchmark_all_ntu60.py
 run bench_reference 900 python bench.py --impl reference --steps 3 --warmup 1
 COSK_NCU=1 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \

@@ -7,7 +7,7 @@ import sys, torch
 sys.path.insert(0, '.')
 import continual_skeletons_b200 as cs
 torch.manual_seed(0)
-for cls in (cs.CoStGcn, cs.CoStGcnMod, cs.CoAGcn):
+for cls in (cs.CoStGcn, cs.CoStGcnMod, cs.CoAGcn, cs.CoSTr):
     m = cls({"dataset_name": "dummy_ntu"})
     x = torch.rand(7, 3, 30, 25, 2, device='cuda')   # 14 skeletons -> 3 tiles (odd: phantom tile in the pair kernels)
     for t in range(30):
