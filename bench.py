@@ -50,10 +50,11 @@ def set_geometry(workload):
     V, CLASSES, DATASET, DATA_LABEL = GEOMETRY.get(workload, (25, 60, "dummy_ntu", "NTU RGB+D 60 joint stream"))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches
-# listed in profiles/r1h_dram_bytes_per_launch.csv (ncu, --cache-control none); None where no capture exists.
-NCU_TRAFFIC = {"tcn<64>": 565.0e6, "tcn<128>": 1136.0e6, "tcn<256>": 2322.0e6, "gcn<64>": 68.0e6, "gcn<128>": 146.0e6,
-               "gcn<256>": 300.0e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches listed in
+# profiles/r1n_ncu_full_main_summary.csv (ncu --set full of one full step; earlier capture with --cache-control none:
+# profiles/r1h_dram_bytes_per_launch.csv); None where no capture exists.
+NCU_TRAFFIC = {"tcn<64>": 552.0e6, "tcn<128>": 1115.0e6, "tcn<256>": 2256.0e6, "gcn<64>": 59.0e6, "gcn<128>": 158.0e6,
+               "gcn<256>": 387.0e6}
 
 
 def load_peaks():
