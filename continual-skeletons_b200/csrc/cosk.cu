@@ -56,6 +56,10 @@ struct BlockW {
   // tensor-core qkv conv: normalised input rows, q | k | v rows (zero-padded to nq_pad columns), and the conv split into
   // column chunks of a width the single-tap temporal-conv kernel is instantiated for
   bool tc_sa_qkv = false;
+  bool tc_sa_fused = false;  // qkv conv + attention in one kernel (k_tc_sa): q, k, v never leave the SM
+  __nv_bfloat16 *d_sa_fw16 = nullptr;  // qkv weights regrouped per head group: [items][hi: q, k, v | lo: same][cin]
+  float *d_sa_fbias = nullptr;         // [items][96]
+  CUtensorMap map_sa_fw;
   ActBuf sa_x, sa_q;
   int nq_pad = 0, n_qchunks = 0;
   struct QChunk {
@@ -101,6 +105,8 @@ struct cosk_model {
   int merge_min_tiles = 4 * 148;  // below this the two CTA groups are not worth splitting (COSK_MERGE_MIN_TILES)
   int merge_split64 = 100;  // CTAs given to the temporal-conv role (64-channel layers)
   int merge_split128 = 92;  // same for the 128-channel layers (CTA pairs)
+  int sa_fused = 1;   // self-attention unit: qkv conv and attention fused in one tcgen05 kernel for C >= 128 (COSK_SA_FUSED=0: separate
+                      // launches everywhere, 2: fused everywhere)
   int sa_qkv_tc = 1;  // qkv conv of the self-attention unit on the tcgen05 single-tap kernel (COSK_SA_QKV_TC=0: fp32 CUDA-core GEMM)
   int attn_tc = 1;  // attention half of the adaptive graph conv on tcgen05 (COSK_ATTN_TC=0: fp32 CUDA-core kernel)
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
@@ -412,6 +418,34 @@ int prepare(cosk_model *m) {
           if ((rc = make_map(m, &qc.map_half, qc.w16, (uint64_t)bc.cin, (uint64_t)2 * qc.width, (uint32_t)qc.width / 2))) return rc;
         }
       }
+      // the fused kernel has eight epilogue warps per SM for the attention math: a win where the q | k | v round trip
+      // dominates (C >= 128), a loss for the 64-channel unit, whose eight tiny heads want the separate kernel's occupancy
+      b.tc_sa_fused = b.tc_sa_qkv && (m->sa_fused == 2 || (m->sa_fused == 1 && bc.cout >= 128));
+      if (b.tc_sa_fused) {
+        const int dk = bc.cout / 4, dvh = bc.cout / 8, dkh = dk / 8, G = 64 / dvh, items = 8 / G;
+        std::vector<float> w((size_t)items * 96 * bc.cin), bb((size_t)items * 96);
+        for (int it = 0; it < items; ++it)
+          for (int r = 0; r < 96; ++r) {
+            int src;  // row of the [q | k | v] conv this column of the item comes from
+            if (r < 16) src = (it * G + r / dkh) * dkh + r % dkh;                       // q of head it*G + r/dkh
+            else if (r < 32) src = dk + (it * G + (r - 16) / dkh) * dkh + (r - 16) % dkh;  // k
+            else src = 2 * dk + (it * G + (r - 32) / dvh) * dvh + (r - 32) % dvh;          // v
+            memcpy(&w[((size_t)it * 96 + r) * bc.cin], &b.sa_qkv_w[(size_t)src * bc.cin], sizeof(float) * bc.cin);
+            bb[(size_t)it * 96 + r] = b.sa_qkv_b[src];
+          }
+        std::vector<uint16_t> st((size_t)items * 192 * bc.cin);
+        for (int it = 0; it < items; ++it)
+          for (int r = 0; r < 96; ++r)
+            for (int k = 0; k < bc.cin; ++k) {
+              const float x = w[((size_t)it * 96 + r) * bc.cin + k];
+              const uint16_t h = f2bf(x);
+              st[((size_t)it * 192 + r) * bc.cin + k] = h;
+              st[((size_t)it * 192 + 96 + r) * bc.cin + k] = f2bf(x - bf2f(h));
+            }
+        if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_sa_fw16), st.data(), st.size()))) return rc;
+        if ((rc = upload(m, b.d_sa_fbias, bb.data(), bb.size()))) return rc;
+        if ((rc = make_map(m, &b.map_sa_fw, b.d_sa_fw16, (uint64_t)bc.cin, (uint64_t)items * 192, 192u))) return rc;
+      }
       // The skip connection is added before the unit's bn, so it enters scaled per channel: a diagonal "residual conv".
       if (!res_conv) {
         std::vector<float> diag((size_t)bc.cin * bc.cout, 0.f);  // k-major [cin][cout]
@@ -567,6 +601,9 @@ int launch_tc_attn(cosk_model *m, const TcAttnArgs &args, cudaStream_t s) {
 
 int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_agcn_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnMaxSmem));
+  CK(cudaFuncSetAttribute(k_tc_sa<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSaCfg<8>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_sa<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSaCfg<16>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_sa<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSaCfg<32>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_attn<16, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<16, 25>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_attn<32, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<32, 25>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_attn<64, 25>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<64, 25>::kSmemBytes));
@@ -754,7 +791,29 @@ int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int 
       CK(launch_k(m, k_sa_affine, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, a));
       m->launches++;
     }
-    for (int q = 0; q < b.n_qchunks; ++q) {  // qkv conv = single-tap temporal-conv kernel without ReLU, per column chunk
+    if (b.tc_sa_fused) {
+      TcSaArgs a;
+      a.tm_x = b.sa_x.map;
+      a.tm_w = b.map_sa_fw;
+      a.x_row = (int)b.sa_x.row_hi(0);
+      a.t_alloc = (int)m->t_alloc;
+      a.cin = bc.cin;
+      a.n_tiles = m->n_tiles;
+      a.tile_tokens = m->tile_tokens;
+      a.V = m->cfg.vertices;
+      a.n_tokens = m->n_tokens;
+      a.bias = b.d_sa_fbias;
+      a.y_hi = b.sa.hi(0);
+      a.y_lo = b.sa.lo(0);
+      a.cs_out = b.sa.cs;
+      a.dbg = m->d_dbg;
+      const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+      if (bc.cout == 64) CK(launch_k(m, k_tc_sa<8>, dim3(grid), dim3(384), TcSaCfg<8>::kSmemBytes, s, a));
+      else if (bc.cout == 128) CK(launch_k(m, k_tc_sa<16>, dim3(grid), dim3(384), TcSaCfg<16>::kSmemBytes, s, a));
+      else CK(launch_k(m, k_tc_sa<32>, dim3(grid), dim3(384), TcSaCfg<32>::kSmemBytes, s, a));
+      m->launches++;
+    }
+    for (int q = 0; !b.tc_sa_fused && q < b.n_qchunks; ++q) {  // qkv conv = single-tap temporal-conv kernel without ReLU, per column chunk
       const BlockW::QChunk &qc = b.qchunk[q];
       TcTcnArgs a;
       a.tm_ring = b.sa_x.map;
@@ -803,7 +862,7 @@ int run_attention_unit(cosk_model *m, int i, const ActBuf &in, int in_slot, int 
     CK(launch_k(m, k_sa_qkv, grid, dim3(256), 0, s, a));
     m->launches++;
   }
-  {
+  if (!b.tc_sa_fused) {
     SaAttnArgs a;
     a.qkv = m->d_qkv;
     a.q_hi = b.tc_sa_qkv ? b.sa_q.hi(0) : nullptr;
@@ -1197,6 +1256,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
   if (const char *e = getenv("COSK_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char *e = getenv("COSK_SA_QKV_TC")) m->sa_qkv_tc = atoi(e);
+  if (const char *e = getenv("COSK_SA_FUSED")) m->sa_fused = atoi(e);
   if (const char *e = getenv("COSK_TCN_IDENTITY_MMA")) m->tcn_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_MERGE")) m->merge = atoi(e);
   if (const char *e = getenv("COSK_MERGE_MIN_TILES")) m->merge_min_tiles = atoi(e);
@@ -1262,6 +1322,8 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_sa_qkv_b);
     dfree(b.d_sa_w16);
     dfree(b.d_res_w_sa);
+    dfree(b.d_sa_fw16);
+    dfree(b.d_sa_fbias);
     for (auto &qc : b.qchunk) {
       dfree(qc.w16);
       dfree(qc.bias);
@@ -1355,9 +1417,11 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
       CK(cudaMemset(m->blk[i].sa.ptr, 0, m->blk[i].sa.bytes()));
       if (m->blk[i].tc_sa_qkv) {
         if ((rc = alloc_act(m, m->blk[i].sa_x, 1, c.blocks[i].cin))) return rc;
-        if ((rc = alloc_act(m, m->blk[i].sa_q, 1, m->blk[i].nq_pad))) return rc;
         CK(cudaMemset(m->blk[i].sa_x.ptr, 0, m->blk[i].sa_x.bytes()));
-        CK(cudaMemset(m->blk[i].sa_q.ptr, 0, m->blk[i].sa_q.bytes()));
+        if (!m->blk[i].tc_sa_fused) {
+          if ((rc = alloc_act(m, m->blk[i].sa_q, 1, m->blk[i].nq_pad))) return rc;
+          CK(cudaMemset(m->blk[i].sa_q.ptr, 0, m->blk[i].sa_q.bytes()));
+        }
       }
     }
   }

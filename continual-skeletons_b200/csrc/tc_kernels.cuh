@@ -1565,6 +1565,261 @@ __global__ void __launch_bounds__(128) k_attn_small(AttnSmallArgs a) {
 }
 
 // =============================================================================================
+// Self-attention unit of CoS-TR, qkv conv + attention in one kernel (GcnUnitAttention / SpatialAttention with
+// only_attention, models/s_tr/s_tr.py:134-231,417-476).  Work item = (token tile, group of G = 64/DVH heads): the
+// mainloop computes the group's [q (16) | k (16) | v (64)] = 96 columns of the qkv conv on tcgen05 (stacked split
+// products: the group's hi and lo weight rows are adjacent, one operand of 192 rows), on the data_bn-normalised input
+// rows.  Two epilogue groups of four warps take alternate items (own TMEM accumulator and shared-memory buffers each;
+// thread = token row): q stays in registers, k and v of the tile go to shared memory as fp32, then per head
+// w_j = softmax_j <q_i, k_j> over the V vertices of the row's skeleton and out_i = sum_j w_j v_j, written as packed
+// split-bf16 rows -- the operand of the unit's output conv.  q, k, v never travel through memory.
+// =============================================================================================
+struct TcSaArgs {
+  CUtensorMap tm_x;  // normalised input rows (1 slot), box {64, 128}
+  CUtensorMap tm_w;  // [items][hi: q, k, v of the group | lo: same][cin], box {64, 192}
+  int x_row, t_alloc, cin;
+  int n_tiles, tile_tokens, V;
+  long long n_tokens;
+  const float *bias;  // [items][96]
+  __nv_bfloat16 *y_hi, *y_lo;
+  int cs_out;
+  unsigned int *dbg;
+};
+
+template <int DVH>
+struct TcSaCfg {
+  static constexpr int kDkh = DVH / 4;
+  static constexpr int kHeadsPerItem = 64 / DVH;  // 8, 4, 2
+  static constexpr int kItems = 8 / kHeadsPerItem;  // per tile: 1, 2, 4
+  static constexpr int kN = 96;                   // q 16 | k 16 | v 64
+  static constexpr int kBBytes = 2 * kN * kBK * 2;  // stacked hi + lo rows: 24 KB
+  static constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  static constexpr int kStageStride = (kStageBytes + 1023) / 1024 * 1024;
+  static constexpr int kStages = 2;
+  static constexpr int kVPitch = 64 + 4;
+  static constexpr int kGroupBytes = kTileRows * 16 * 4 + kTileRows * kVPitch * 4;  // k + v of one epilogue group
+  static constexpr int kKOff = kStages * kStageStride;
+  static constexpr int kBiasOff = kKOff + 2 * kGroupBytes;
+  static constexpr int kBarOff = kBiasOff + 4 * kN * 4;
+  static constexpr int kSmemBytes = kBarOff + 128 + 1024;
+  static constexpr int kAccStride = 256;
+  static constexpr int kTmemCols = 512;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+};
+
+template <int DVH>
+__global__ void __launch_bounds__(384, 1) k_tc_sa(const __grid_constant__ TcSaArgs a) {
+  using Cfg = TcSaCfg<DVH>;
+  constexpr int DKH = Cfg::kDkh, G = Cfg::kHeadsPerItem, NI = Cfg::kItems, N = Cfg::kN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);  // [NI][96]
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::kBarOff);
+  uint64_t *empty = full + Cfg::kStages;
+  uint64_t *tfull = empty + Cfg::kStages;
+  uint64_t *tempty = tfull + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull[s], 1);
+      ptx::mbar_init(&tempty[s], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&a.tm_x);
+    ptx::prefetch_tmap(&a.tm_w);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < NI * N; i += blockDim.x) bias_s[i] = a.bias[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int nkb = a.cin / kBK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+        const int row = a.x_row + tile * a.tile_tokens;
+        for (int item = 0; ok && item < NI; ++item) {
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&empty[ps.stage], ps.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)(item * 16 + kc));
+            if (!ok) break;
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageStride;
+            ptx::mbar_arrive_expect_tx(&full[ps.stage], Cfg::kStageBytes);
+            ptx::tma_load_2d_hint(st, &a.tm_x, &full[ps.stage], kc * kBK, row, ptx::kEvictNormal);
+            ptx::tma_load_2d_hint(st + kABytes, &a.tm_x, &full[ps.stage], kc * kBK, row + a.t_alloc, ptx::kEvictNormal);
+            ptx::tma_load_2d_hint(st + 2 * kABytes, &a.tm_w, &full[ps.stage], kc * kBK, item * 2 * N, ptx::kEvictLast);
+            ps.advance<Cfg::kStages>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      bool ok = true;
+      int it = 0;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+        for (int item = 0; ok && item < NI; ++item, ++it) {
+          const int acc = it & 1;
+          ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
+          if (!ok) break;
+          ptx::tc_fence_after();
+          const uint32_t d = tmem_base + acc * Cfg::kAccStride;
+          for (int kc = 0; kc < nkb; ++kc) {
+            ok = ptx::mbar_wait(&full[ps.stage], ps.phase, a.dbg, kDbgMmaFull | (unsigned)(item * 16 + kc));
+            if (!ok) break;
+            ptx::tc_fence_after();
+            const uint32_t st = smem_base + ps.stage * Cfg::kStageStride;
+            issue_kblock_stacked<2 * N>(d, st, st + kABytes, st + 2 * kABytes, kc == 0);
+            ptx::umma_commit(&empty[ps.stage]);
+            ps.advance<Cfg::kStages>();
+          }
+          if (ok) ptx::umma_commit(&tfull[acc]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool row_ok = row < a.tile_tokens;
+    const int sk0 = row_ok ? row - row % a.V : 0;
+    float *k_s = reinterpret_cast<float *>(smem + Cfg::kKOff + grp * Cfg::kGroupBytes);  // [128][16]
+    float *v_s = k_s + kTileRows * 16;                                                    // [128][kVPitch]
+    bool ok = true;
+    int it = 0;
+    for (int tile = cta; tile < a.n_tiles; tile += ncta) {
+      const long long tok = (long long)tile * a.tile_tokens + row;
+      const bool valid = row_ok && tok < a.n_tokens;
+      for (int item = 0; item < NI; ++item, ++it) {
+        const int acc = it & 1;
+        if (acc != grp) continue;
+        float qv[16];
+        if (ok) ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
+        if (ok) {
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccStride;
+          const float *bb = bias_s + item * N;
+#pragma unroll 1
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t yh[16], yl[16];
+            ptx::tmem_ld_32x16(taddr + c0, yh);
+            ptx::tmem_ld_32x16(taddr + N + c0, yl);
+            ptx::tmem_ld_wait();
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(yh[j]) + __uint_as_float(yl[j]) + bb[c0 + j];
+            if (c0 == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) qv[j] = x[j];
+            } else if (c0 == 16) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4 *>(k_s + row * 16 + 4 * j4) = make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+            } else {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4)
+                *reinterpret_cast<float4 *>(v_s + row * Cfg::kVPitch + (c0 - 32) + 4 * j4) =
+                    make_float4(x[4 * j4], x[4 * j4 + 1], x[4 * j4 + 2], x[4 * j4 + 3]);
+            }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);  // accumulator drained: the next item's MMAs may start
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // k / v of the whole tile are in shared memory
+        if (ok && valid) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {  // unrolled: q stays in registers
+            float w[kAttnMaxV];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kAttnMaxV; ++j) {
+              if (j < a.V) {
+                float sdot = 0.f;
+                if (DKH >= 4) {
+#pragma unroll
+                  for (int d4 = 0; d4 < DKH / 4; ++d4) {
+                    const float4 k4 = *reinterpret_cast<const float4 *>(k_s + (sk0 + j) * 16 + g * DKH + 4 * d4);
+                    sdot = fmaf(qv[g * DKH + 4 * d4], k4.x, sdot);
+                    sdot = fmaf(qv[g * DKH + 4 * d4 + 1], k4.y, sdot);
+                    sdot = fmaf(qv[g * DKH + 4 * d4 + 2], k4.z, sdot);
+                    sdot = fmaf(qv[g * DKH + 4 * d4 + 3], k4.w, sdot);
+                  }
+                } else {
+                  const float2 k2 = *reinterpret_cast<const float2 *>(k_s + (sk0 + j) * 16 + g * 2);
+                  sdot = fmaf(qv[g * 2], k2.x, qv[g * 2 + 1] * k2.y);
+                }
+                w[j] = sdot;
+                mx = fmaxf(mx, sdot);
+              } else {
+                w[j] = 0.f;
+              }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < kAttnMaxV; ++j)
+              if (j < a.V) {
+                w[j] = expf(w[j] - mx);
+                sum += w[j];
+              }
+            const float inv = 1.0f / sum;
+            float o[DVH];
+#pragma unroll
+            for (int d = 0; d < DVH; ++d) o[d] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kAttnMaxV; ++j)
+              if (j < a.V) {
+                const float wj = w[j] * inv;
+#pragma unroll
+                for (int d4 = 0; d4 < DVH / 4; ++d4) {
+                  const float4 v4 = *reinterpret_cast<const float4 *>(v_s + (sk0 + j) * Cfg::kVPitch + g * DVH + 4 * d4);
+                  o[4 * d4] = fmaf(wj, v4.x, o[4 * d4]);
+                  o[4 * d4 + 1] = fmaf(wj, v4.y, o[4 * d4 + 1]);
+                  o[4 * d4 + 2] = fmaf(wj, v4.z, o[4 * d4 + 2]);
+                  o[4 * d4 + 3] = fmaf(wj, v4.w, o[4 * d4 + 3]);
+                }
+              }
+            const int col = (item * G + g) * DVH;
+#pragma unroll
+            for (int e = 0; e < DVH / 8; ++e) {
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int w2 = 0; w2 < 4; ++w2) {
+                const float x0 = o[8 * e + 2 * w2], x1 = o[8 * e + 2 * w2 + 1];
+                oh[w2] = pack_bf16x2(x0, x1);
+                ol[w2] = pack_bf16x2(x0 - bf16_lo_as_float(oh[w2]), x1 - bf16_hi_as_float(oh[w2]));
+              }
+              *reinterpret_cast<uint4 *>(a.y_hi + tok * a.cs_out + col + 8 * e) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4 *>(a.y_lo + tok * a.cs_out + col + 8 * e) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            }
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // buffers free for the group's next item
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// =============================================================================================
 // One launch, two roles: CTAs [0, n_tcn) run the temporal conv of block L, the remaining CTAs the graph
 // conv of block L+1, which consumes the temporal conv's output tile by tile (per-tile release/acquire
 // counters in global memory).  The temporal convs of the 64- and 128-channel layers are bound by HBM and
