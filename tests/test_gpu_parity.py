@@ -515,3 +515,29 @@ def test_cos_tr_schedule_and_replicas():
     big = m.forward_steps(base.repeat(reps, 1, 1, 1, 1))
     assert m.device_error() == 0
     assert torch.equal(big.view(reps, 2, 400), small.unsqueeze(0).expand(reps, 2, 400))
+
+
+@pytest.mark.parametrize("mode", ["clip", "frame"])
+def test_forward_call_modes(golden, mode):
+    """CoModelBase.forward (models/base.py:166-181): in "clip" mode the first prediction of the padded regular
+    network, in "frame" mode a reset followed by forward_steps -- both equal the reference-block fixture; with
+    profile_model the state is kept between calls and warm_up makes every `stride`-frame call yield a prediction."""
+    arch = weights.cost_gcn_arch()
+    sd = weights.make_state_dict(arch, seed=7, randomize=False)
+    m = cs.CoStGcn({"dataset_name": "dummy_ntu", "forward_mode": mode})
+    m.load_state_dict(m.map_state_dict(sd), strict=True)
+    assert m.call_mode == ("forward_steps" if mode == "frame" else "forward")
+    x = weights.make_input((2, 3, 300, 25, 2), seed=11).to(DEV)
+    want = torch.from_numpy(golden["cost_gcn"]["cost_gcn_co_logits"])
+    for _ in range(2):  # a second call starts from a clean state again
+        out = m(x)
+        assert tuple(out.shape) == (2, 60)
+        assert float((out.cpu() - want).abs().max()) <= 1e-3
+    if mode == "frame":
+        p = cs.CoStGcn({"dataset_name": "dummy_ntu", "forward_mode": "frame", "profile_model": True})
+        assert p.input_shape == (3, p.stride, 25, 2)
+        sample = torch.rand((2,) + p.input_shape, device=DEV)
+        p.warm_up(None, sample)
+        for _ in range(3):
+            o = p(sample)
+            assert o is not None and tuple(o.shape) == (2, 60)
