@@ -111,7 +111,7 @@ struct cosk_model {
   int attn_tc = 1;  // attention half of the adaptive graph conv on tcgen05 (COSK_ATTN_TC=0: fp32 CUDA-core kernel)
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
-  int pdl = 0;  // programmatic dependent launch between the kernels of a step (measured ~4% slower on B200 at 4096 streams, so off); COSK_PDL=1 enables
+  int pdl = 1;  // programmatic dependent launch between the kernels of a step: +16 % at 256 streams, +4 % at 1024, neutral at 4096 (COSK_PDL=0 disables)
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
   std::vector<BlockW> blk;
