@@ -541,3 +541,34 @@ def test_forward_call_modes(golden, mode):
         for _ in range(3):
             o = p(sample)
             assert o is not None and tuple(o.shape) == (2, 60)
+
+
+@pytest.mark.parametrize("n_streams", [1, 5])
+@pytest.mark.parametrize("which", ["coa_gcn", "cos_tr"])
+def test_widened_models_ragged_tiles(which, n_streams):
+    """Odd stream counts (1 and 5 streams: a single partly filled tile, and skeletons that straddle tiles) through the
+    attention / dense-mix kernels: every block's latest output against the step oracle's clip-layout features."""
+    if which == "coa_gcn":
+        arch, sd, m = _load_model(cs.CoAGcn, weights.coa_gcn_arch, True)
+        V = 25
+    else:
+        arch, sd, m = _load_cos_tr(True)
+        V = 18
+    T = 34
+    x = weights.make_input((n_streams, 3, T, V, 2), seed=21)
+    with torch.no_grad():
+        feats = []
+        regular.stack_features(regular.normalise_input(x, sd), sd, arch, feats, per_frame=True)
+    ref = step.StepModel(sd, arch)
+    xd = x.to(DEV)
+    for t in range(T):
+        with torch.no_grad():
+            ref.forward_step(x[:, :, t])
+        m.forward_step(xd[:, :, t].contiguous())
+        assert m.last_schedule() == ref.trace[-1], t
+    assert m.device_error() == 0
+    for i in range(10):
+        n_out = sum(1 for f in ref.trace if f[i])
+        if n_out:
+            e = _rel_err(m.read_block(i).cpu(), feats[i][:, :, n_out - 1])
+            assert e < 2e-4, (which, n_streams, i, e)
