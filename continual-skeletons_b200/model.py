@@ -681,6 +681,10 @@ class CoSTr(CoModelBase):
         specs = super().block_specs(c_in)
         return specs[:3] + [sp._replace(gconv="attention") for sp in specs[3:]]
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """CoSTr maps regular S-TR keys by itself when loading (models/cos_tr/cos_tr.py:73-79)."""
+        return super().load_state_dict(self.map_state_dict(state_dict, strict), strict=strict, **kw)
+
 
 # ---------------------------------------------------------------------------------------------
 # headless stack of blocks (what the reference's block-level tests build with co.Sequential)

@@ -259,6 +259,8 @@ def test_cos_tr_host_model(golden):
     sd = weights.make_state_dict(arch, seed=8, randomize=True)
     res = m.load_state_dict(m.map_state_dict(sd), strict=True)
     assert not res.missing_keys and not res.unexpected_keys
+    res = cs.CoSTr({"dataset_name": "dummy_kin"}).load_state_dict(sd, strict=True)  # regular keys are mapped on load (cos_tr.py:73-79)
+    assert not res.missing_keys and not res.unexpected_keys
     from continual_skeletons_b200 import model as _m
 
     blk, spec = m.layers.layer6, m._specs[5]
