@@ -40,7 +40,8 @@ ALGO = {
     "cos_tr": {"state": 1.408e6 * 18 / 25, "io": 432 + 1600 / 4 + 2048 / 4, "flops": 0.16e9 / 4 * 2, "warm": 297, "period": 4},
 }
 NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*", "coa_gcn": "CoA-GCN", "cos_tr": "CoS-TR"}
-GEOMETRY = {"cos_tr": (18, 400, "dummy_kin", "Kinetics-400 skeleton")}  # workload -> V, classes, dataset, label
+# workload -> V, classes, dataset, label (BASELINE configs[2] quotes CoA-GCN on NTU RGB+D 120, configs[3] CoS-TR on Kinetics)
+GEOMETRY = {"cos_tr": (18, 400, "dummy_kin", "Kinetics-400 skeleton"), "coa_gcn": (25, 120, "ntu120", "NTU RGB+D 120 joint stream")}
 DATASET, DATA_LABEL = "dummy_ntu", "NTU RGB+D 60 joint stream"
 
 
@@ -116,8 +117,8 @@ def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
 
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    arch = {"cost_gcn": weights.cost_gcn_arch, "cost_gcn_mod": weights.cost_gcn_mod_arch, "coa_gcn": weights.coa_gcn_arch,
-            "cos_tr": weights.cos_tr_arch}[workload]()
+    arch = {"cost_gcn": weights.cost_gcn_arch, "cost_gcn_mod": weights.cost_gcn_mod_arch, "cos_tr": weights.cos_tr_arch,
+            "coa_gcn": lambda: weights.coa_gcn_arch(classes=120)}[workload]()
     sd = weights.make_state_dict(arch, seed=0)
     model = step.StepModel(sd, arch)
     frames = [torch.rand(n_streams, C_IN, V, S) for _ in range(4)]
@@ -144,7 +145,7 @@ def run_reference(args, rank, world):
     sample = (f"{n_sample} concurrent streams per step (bounded sample of the {args.streams}-stream workload), steady state "
               f"after {ALGO[args.workload]['warm']} warm frames, oracle/step.py eager torch fp32")
     line = {
-        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU60"), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU120" if CLASSES == 120 else "NTU60"), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "p50_ms_per_step": p50, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -330,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
     traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 and V == 25 and not (args.workload == "coa_gcn" and kname == "gcn") else None
     step_bytes = algo["state"] + algo["io"]
     line = {
-        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU60"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU120" if CLASSES == 120 else "NTU60"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, f32 accumulate)" if args.kernel_path == "auto" else "f32",
         "data": "synthetic", "config": make_config(args, world),
