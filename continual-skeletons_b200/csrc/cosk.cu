@@ -16,6 +16,7 @@
 
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_gcnp.cuh"
 
 using namespace cosk;
 
@@ -76,6 +77,11 @@ struct BlockW {
   __nv_bfloat16 *d_gcn_w16 = nullptr, *d_tcn_w16 = nullptr, *d_att_w16 = nullptr;
   CUtensorMap map_gcn_w, map_tcn_w, map_tcn_w_half, map_att_w;  // _half: box of cout/2 rows for the CTA-pair kernel
   bool tc_gcn = false, tc_tcn = false;
+  // pre-mix graph conv (k_tc_gcnp): weights [2*cout rows (hi, lo)][gcnp_parts*cin], partition-major K
+  bool tc_gcnp = false, gcnp_stacked = false, gcnp_unit_diag = false;
+  int gcnp_parts = 3;
+  __nv_bfloat16 *d_gcnp_w16 = nullptr;
+  CUtensorMap map_gcnp_w;
   bool tc_attn = false;  // adaptive graph conv: attention half on the tcgen05 kernel
   bool gcn_res_in_mix = false;  // P = 3 plain graph conv: identity residual added by the mix warps (else by the drain warps)
   bool tcn_res_kblock = false;  // tensor-core temporal conv: the residual enters as extra K-blocks of the GEMM (folded
@@ -112,6 +118,10 @@ struct cosk_model {
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
   int pdl = 1;  // programmatic dependent launch between the kernels of a step: +16 % at 256 streams, +4 % at 1024, neutral at 4096 (COSK_PDL=0 disables)
+  int gcn_premix = 7;  // which plain graph-conv widths run on the pre-mix / A-in-TMEM kernel k_tc_gcnp (bit 0: 64, bit 1: 128,
+                       // bit 2: 256 output channels); the rest stays on k_tc_gcn (COSK_GCN_PREMIX)
+  int gcnp_identity_mma = 3;  // widths whose identity gcn_residual rides in the pre-mix GEMM as a 4th part (same bits; others: epilogue add)
+  int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
   std::vector<BlockW> blk;
@@ -130,6 +140,8 @@ struct cosk_model {
   long long pool_n = 0, frame = 0;
   std::vector<int32_t> last_flags;
   unsigned int *d_dbg = nullptr;
+  unsigned int *h_dbg = nullptr;  // pinned copy of d_dbg, refreshed asynchronously after every emitting step
+  bool failed = false;            // a step stopped half way or the device watchdog fired: only cosk_reset / cosk_set_batch clear it
   unsigned long long *d_trace = nullptr;  // phase timers of the graph-conv kernel (COSK_TRACE=1)
   int64_t launches = 0;
   int64_t state_bytes = 0;
@@ -142,6 +154,20 @@ struct cosk_model {
 };
 
 namespace {
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it
+// (a host process may hold handles on several GPUs, and PyTorch tracks the current device per thread).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 int fail(cosk_model *m, int code, const char *fmt, ...) {
   char buf[512];
@@ -387,6 +413,30 @@ int prepare(cosk_model *m) {
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
       if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
     }
+    {
+      // pre-mix kernel: sources per (partition >= 1, output vertex) must fit its register CSR
+      int part_max = 0;
+      for (int p = 1; p < 3; ++p)
+        for (int w = 0; w < V; ++w) part_max = std::max(part_max, ptr[p * V + w + 1] - ptr[p * V + w]);
+      const int wbit = bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4;
+      b.tc_gcnp = b.tc_gcn && !adaptive && !attention && tc_width(bc.cout) && (m->gcn_premix & wbit) && part_max <= kPartSrcMax;
+      if (b.tc_gcnp) {
+        const bool ident_mma = !res_conv && (m->gcnp_identity_mma & wbit);
+        const int P = b.gcnp_parts = (res_conv || ident_mma) ? 4 : 3;
+        const int K = P * bc.cin;
+        std::vector<float> w((size_t)bc.cout * K, 0.f);
+        for (int o = 0; o < bc.cout; ++o) {
+          memcpy(&w[(size_t)o * K], &b.gcn_w[(size_t)o * Kg], sizeof(float) * std::min(K, Kg));
+          if (ident_mma) w[(size_t)o * K + 3 * bc.cin + o] = 1.0f;
+        }
+        std::vector<uint16_t> s = split_rows(w, bc.cout, K);
+        if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcnp_w16), s.data(), s.size()))) return rc;
+        if ((rc = make_map(m, &b.map_gcnp_w, b.d_gcnp_w16, (uint64_t)K, (uint64_t)2 * bc.cout, (uint32_t)std::min(2 * bc.cout, 256)))) return rc;
+        b.gcnp_stacked = bc.cout <= 128 && (m->gcnp_stacked & wbit);
+        b.gcnp_unit_diag = true;
+        for (int w0 = 0; w0 < V; ++w0) b.gcnp_unit_diag &= (ptr[w0 + 1] - ptr[w0] == 1 && val[ptr[w0]] == 1.0f);
+      }
+    }
     if (attention) {
       std::vector<float> tq = transpose(b.sa_qkv_w.data(), 2 * (bc.cout / 4) + bc.cout, bc.cin);
       if ((rc = upload(m, b.d_sa_qkv_w, tq.data(), tq.size()))) return rc;
@@ -526,6 +576,8 @@ int zero_state(cosk_model *m, cudaStream_t s) {
     CK(cudaMemsetAsync(m->d_pool_sum, 0, (size_t)m->n_streams * cl * sizeof(double), s));
   }
   CK(cudaMemsetAsync(m->d_dbg, 0, 4 * sizeof(unsigned int), s));
+  if (m->h_dbg) m->h_dbg[0] = 0;
+  m->failed = false;
   m->pool_n = 0;
   m->frame = 0;
   std::fill(m->last_flags.begin(), m->last_flags.end(), 0);
@@ -628,6 +680,11 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcn<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnCfg<4, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnp<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<64, true>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnp<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<64, false>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnp<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, true>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnp<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, false>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnp<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<256, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn_gcn<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           std::max(TcTcnCfg<64>::kSmemBytes, TcGcnCfg<4, 1>::kSmemBytes)));
   CK(cudaFuncSetAttribute(k_tc_tcn2_gcn<128, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -670,6 +727,43 @@ TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int
   return a;
 }
 
+TcGcnpArgs make_gcnp_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  BlockW &b = m->blk[i];
+  TcGcnpArgs a;
+  a.tm_x = in.map;
+  a.tm_w = b.map_gcnp_w;
+  a.x_row = (int)in.row_hi(in_slot);
+  a.t_alloc = (int)m->t_alloc;
+  a.cin = bc.cin;
+  a.n_parts = b.gcnp_parts;
+  a.V = m->cfg.vertices;
+  a.n_tiles = m->n_tiles;
+  a.tile_tokens = m->tile_tokens;
+  a.n_tokens = m->n_tokens;
+  a.mix_ptr = b.d_mix_ptr;
+  a.mix_src = b.d_mix_src;
+  a.mix_val = b.d_mix_val;
+  a.unit_diag = b.gcnp_unit_diag ? 1 : 0;
+  a.epi.bias = b.d_gcn_b;
+  const bool epi_res = b.gcnp_parts == 3;  // identity gcn_residual added by the epilogue from the input rows
+  a.epi.r_hi = epi_res ? in.hi(in_slot) : nullptr;
+  a.epi.r_lo = epi_res ? in.lo(in_slot) : nullptr;
+  a.epi.cs_r = in.cs;
+  a.epi.y_hi = b.ring.hi(ring_slot);
+  a.epi.y_lo = b.ring.lo(ring_slot);
+  a.epi.cs_out = b.ring.cs;
+  a.dbg = m->d_dbg;
+  return a;
+}
+
+template <int COUT, bool STACKED>
+int launch_tc_gcnp(cosk_model *m, const TcGcnpArgs &args, cudaStream_t s) {
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  CK(launch_k(m, k_tc_gcnp<COUT, STACKED>, dim3(grid), dim3(512), TcGcnpCfg<COUT, STACKED>::kSmemBytes, s, args));
+  return COSK_OK;
+}
+
 TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, int out_slot) {
   const cosk_block_cfg &bc = m->cfg.blocks[i];
   BlockW &b = m->blk[i];
@@ -708,7 +802,7 @@ bool can_merge(const cosk_model *m, int i) {
   if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.blocks[i + 1].gconv != COSK_GCONV_PLAIN) return false;
   const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
   const int c = m->cfg.blocks[i].cout;
-  if (!b.tc_tcn || !nb.tc_gcn || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
+  if (!b.tc_tcn || !nb.tc_gcn || nb.tc_gcnp || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
   if (m->n_tiles < m->merge_min_tiles) return false;
   if (c == 64) return m->gcn_single_stage && !(m->pair_mask & 1);
   if (c == 128) return (m->pair_mask & 2) != 0;
@@ -1016,6 +1110,12 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     if (b.gcn_parts == 4) rc = v25 ? launch_tc_agcn<4, 1, 25>(m, a, s) : launch_tc_agcn<4, 1, 18>(m, a, s);
     else rc = v25 ? launch_tc_agcn<3, 2, 25>(m, a, s) : launch_tc_agcn<3, 2, 18>(m, a, s);
     if (rc) return rc;
+  } else if (b.tc_gcnp) {
+    TcGcnpArgs a = make_gcnp_args(m, i, in, in_slot, ring_slot);
+    if (bc.cout == 64) rc = b.gcnp_stacked ? launch_tc_gcnp<64, true>(m, a, s) : launch_tc_gcnp<64, false>(m, a, s);
+    else if (bc.cout == 128) rc = b.gcnp_stacked ? launch_tc_gcnp<128, true>(m, a, s) : launch_tc_gcnp<128, false>(m, a, s);
+    else rc = launch_tc_gcnp<256, false>(m, a, s);
+    if (rc) return rc;
   } else if (b.tc_gcn) {
     TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
     // one K-block per work item (cin = 64): single operand stage, four exchange buffers
@@ -1247,12 +1347,15 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
     delete m;
     return COSK_ERR_CUDA;  // no CPU fallback: the library is useless without a CUDA device
   }
-  cudaSetDevice(cfg->device);
+  DeviceGuard guard_(cfg->device);
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, cfg->device);
   m->num_sms = prop.multiProcessorCount;
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
+  if (const char *e = getenv("COSK_GCN_PREMIX")) m->gcn_premix = atoi(e);
+  if (const char *e = getenv("COSK_GCNP_IDENTITY_MMA")) m->gcnp_identity_mma = atoi(e);
+  if (const char *e = getenv("COSK_GCNP_STACKED")) m->gcnp_stacked = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
   if (const char *e = getenv("COSK_ATTN_TC")) m->attn_tc = atoi(e);
   if (const char *e = getenv("COSK_SA_QKV_TC")) m->sa_qkv_tc = atoi(e);
@@ -1287,9 +1390,16 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
     return COSK_ERR_CUDA;
   }
   cudaMemset(m->d_dbg, 0, 4 * sizeof(unsigned int));
+  if (cudaHostAlloc(&m->h_dbg, 4 * sizeof(unsigned int), cudaHostAllocDefault) != cudaSuccess) {
+    cudaFree(m->d_dbg);
+    delete m;
+    return COSK_ERR_CUDA;
+  }
+  memset(m->h_dbg, 0, 4 * sizeof(unsigned int));
   if (sm100 && set_smem_attrs(m) != COSK_OK) {
     fprintf(stderr, "cosk_create: %s\n", m->err.c_str());
     cudaFree(m->d_dbg);
+    cudaFreeHost(m->h_dbg);
     delete m;
     return COSK_ERR_CUDA;
   }
@@ -1299,7 +1409,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
 
 void cosk_destroy(cosk_model *m) {
   if (!m) return;
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   free_state(m);
   for (auto &b : m->blk) {
     dfree(b.d_gcn_w);
@@ -1314,6 +1424,7 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_att_b);
     dfree(b.d_adj);
     dfree(b.d_gcn_w16);
+    dfree(b.d_gcnp_w16);
     dfree(b.d_tcn_w16);
     dfree(b.d_att_w16);
     dfree(b.d_sa_scale);
@@ -1334,6 +1445,7 @@ void cosk_destroy(cosk_model *m) {
   dfree(m->d_fc_w);
   dfree(m->d_fc_b);
   dfree(m->d_dbg);
+  if (m->h_dbg) cudaFreeHost(m->h_dbg);
   dfree(m->d_trace);
   for (auto e : m->ev_pool) cudaEventDestroy(e);
   delete m;
@@ -1377,7 +1489,7 @@ int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t
 
 int cosk_set_batch(cosk_model *m, int64_t n_streams) {
   if (!m || n_streams < 1) return COSK_ERR_ARG;
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   if (!m->prepared) {
     int rc = prepare(m);
     if (rc) return rc;
@@ -1446,7 +1558,7 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
 int cosk_reset(cosk_model *m) {
   if (!m) return COSK_ERR_ARG;
   if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_reset before cosk_set_batch");
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   CK(cudaDeviceSynchronize());
   int rc = zero_state(m, 0);
   if (rc) return rc;
@@ -1454,26 +1566,63 @@ int cosk_reset(cosk_model *m) {
   return COSK_OK;
 }
 
+// Shared entry checks of cosk_step / cosk_steps: call order, and the failure latch.  A step that stopped half way
+// leaves the host counters ahead of the device state, and a fired pipeline watchdog (bounded mbarrier wait,
+// ptx.cuh) makes every later result garbage: both refuse further steps until cosk_reset / cosk_set_batch.
+static int step_entry(cosk_model *m) {
+  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "step before cosk_set_batch");
+  if (!m->prepared) return fail(m, COSK_ERR_STATE, "weights changed after cosk_set_batch: call cosk_set_batch again");
+  if (m->h_dbg && m->h_dbg[0] != 0) m->failed = true;  // written by the async copy behind an earlier emitting step
+  if (m->failed) {
+    if (m->h_dbg && m->h_dbg[0] != 0)
+      return fail(m, COSK_ERR_STATE, "device pipeline watchdog fired (code 0x%08x): results since then are invalid; cosk_reset to continue",
+                  m->h_dbg[0]);
+    return fail(m, COSK_ERR_STATE, "an earlier step failed half way: state and schedule are out of step; cosk_reset to continue");
+  }
+  return COSK_OK;
+}
+
+static int step_guarded(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s) {
+  int32_t em = 0;
+  int rc = step_impl(m, x, nc_stride, out, &em, s);
+  if (rc) {
+    m->failed = true;  // counters may be partly advanced
+    return rc;
+  }
+  if (em && m->h_dbg) {
+    // surface the watchdog word without a host sync: it lands in pinned memory behind this step's kernels and is
+    // looked at on the next call
+    if (cudaMemcpyAsync(m->h_dbg, m->d_dbg, sizeof(unsigned int), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+      m->failed = true;
+      return fail(m, COSK_ERR_CUDA, "cudaMemcpyAsync of the watchdog word failed");
+    }
+  }
+  if (emitted) *emitted = em;
+  return COSK_OK;
+}
+
 int cosk_step(cosk_model *m, const float *x_dev, int64_t nc_stride, float *out_dev, int32_t *emitted, void *stream) {
   if (!m || !x_dev || !out_dev) return COSK_ERR_ARG;
-  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_step before cosk_set_batch");
-  cudaSetDevice(m->cfg.device);
-  return step_impl(m, x_dev, nc_stride, out_dev, emitted, (cudaStream_t)stream);
+  int rc = step_entry(m);
+  if (rc) return rc;
+  DeviceGuard guard_(m->cfg.device);
+  return step_guarded(m, x_dev, nc_stride, out_dev, emitted, (cudaStream_t)stream);
 }
 
 int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride, int32_t max_out,
                int32_t *n_emitted, void *stream) {
   if (!m || !x_dev || !out_dev || T < 0) return COSK_ERR_ARG;
-  if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_steps before cosk_set_batch");
-  cudaSetDevice(m->cfg.device);
+  int rc = step_entry(m);
+  if (rc) return rc;
+  DeviceGuard guard_(m->cfg.device);
   const long long frame_elems = (long long)m->cfg.vertices * m->cfg.persons;
   int32_t cnt = 0;
   for (int t = 0; t < T; ++t) {
     int32_t em = 0;
     // once max_out emissions are stored, later ones land in the last slot
     const int32_t dst = cnt < max_out ? cnt : max_out - 1;
-    int rc = step_impl(m, x_dev + t * frame_elems, (long long)T * frame_elems, out_dev + (long long)dst * out_stride, &em,
-                       (cudaStream_t)stream);
+    rc = step_guarded(m, x_dev + t * frame_elems, (long long)T * frame_elems, out_dev + (long long)dst * out_stride, &em,
+                      (cudaStream_t)stream);
     if (rc) return rc;
     cnt += em;
   }
@@ -1496,7 +1645,7 @@ int cosk_read_block(cosk_model *m, int32_t block, float *dst_dev, void *stream) 
   if (m->n_streams == 0) return fail(m, COSK_ERR_STATE, "cosk_read_block before cosk_set_batch");
   const BlockW &b = m->blk[block];
   if (b.n_out == 0) return fail(m, COSK_ERR_STATE, "block %d has not emitted yet", block);
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   const int slot = (int)((b.n_out - 1) % kOutSlots);
   const long long total = m->n_tokens * b.out.c;
   CK(launch_k(m, k_read_block, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
@@ -1515,7 +1664,7 @@ int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block) {
 
 int cosk_device_error(cosk_model *m, uint32_t *code) {
   if (!m || !code) return COSK_ERR_ARG;
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   unsigned int h[4] = {0, 0, 0, 0};
   CK(cudaMemcpy(h, m->d_dbg, sizeof h, cudaMemcpyDeviceToHost));
   *code = h[0];
@@ -1549,7 +1698,7 @@ int cosk_simulate_schedule(const cosk_config *cfg, int32_t T, int32_t *flags) {
 int cosk_trace_read(cosk_model *m, uint64_t *out, int32_t n) {
   if (!m || !out || n < 1) return COSK_ERR_ARG;
   if (!m->d_trace) return fail(m, COSK_ERR_STATE, "tracing is off (set COSK_TRACE=1 before cosk_create)");
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   CK(cudaMemcpy(out, m->d_trace, sizeof(uint64_t) * (size_t)(n < 64 ? n : 64), cudaMemcpyDeviceToHost));
   return COSK_OK;
 }
@@ -1564,7 +1713,7 @@ int cosk_profile_enable(cosk_model *m, int32_t on) {
 
 int cosk_profile_read(cosk_model *m, int32_t kind, int32_t block, double *ms, int64_t *launches) {
   if (!m || !ms || !launches) return COSK_ERR_ARG;
-  cudaSetDevice(m->cfg.device);
+  DeviceGuard guard_(m->cfg.device);
   double tot = 0.0;
   int64_t cnt = 0;
   for (size_t i = 0; i + 1 < m->prof.size(); ++i) {

@@ -476,8 +476,12 @@ class _CoBase(nn.Module):
         self._ensure_batch(e, (n_streams,) + tuple(x.shape[1:]), n_streams)
         out = torch.empty(self._out_shape(n_streams), dtype=torch.float32, device=x.device)
         em = ctypes.c_int32(0)
-        e.check(e.lib.cosk_step(e.h, ctypes.c_void_p(x.data_ptr()), nc_stride, ctypes.c_void_p(out.data_ptr()),
-                                ctypes.byref(em), self._stream(x)), "cosk_step")
+        try:
+            e.check(e.lib.cosk_step(e.h, ctypes.c_void_p(x.data_ptr()), nc_stride, ctypes.c_void_p(out.data_ptr()),
+                                    ctypes.byref(em), self._stream(x)), "cosk_step")
+        except CoskError:
+            self._shape = None  # the handle latched a failure: the next call re-creates (and zeroes) all state
+            raise
         return out if em.value else None
 
     def _steps(self, x, n_streams, T, shape_key):
@@ -488,8 +492,12 @@ class _CoBase(nn.Module):
         oshape = self._out_shape(n_streams)
         out = torch.empty((max_out,) + oshape, dtype=torch.float32, device=x.device)
         n = ctypes.c_int32(0)
-        e.check(e.lib.cosk_steps(e.h, ctypes.c_void_p(x.data_ptr()), T, ctypes.c_void_p(out.data_ptr()),
-                                 int(np.prod(oshape)), max_out, ctypes.byref(n), self._stream(x)), "cosk_steps")
+        try:
+            e.check(e.lib.cosk_steps(e.h, ctypes.c_void_p(x.data_ptr()), T, ctypes.c_void_p(out.data_ptr()),
+                                     int(np.prod(oshape)), max_out, ctypes.byref(n), self._stream(x)), "cosk_steps")
+        except CoskError:
+            self._shape = None
+            raise
         if n.value == 0:
             return None
         return out[: n.value]
@@ -665,9 +673,21 @@ class CoStGcnMod(CoModelBase):
 
 class CoAGcn(CoModelBase):
     """CoA-GCN: the CoST-GCN geometry with ``AdaptiveGraphConvolution`` stepped one frame at a time
-    (models/coa_gcn/coa_gcn.py:11-46; the vertex attention of a step sees that step's frame only)."""
+    (models/coa_gcn/coa_gcn.py:11-46; the vertex attention of a step sees that step's frame only).
+
+    Only the per-step semantics are implemented: ``forward_step`` / ``forward_steps`` / ``forward`` in
+    ``forward_mode="frame"``.  The reference's CLIP forward of this model is a different function -- it runs
+    ``AdaptiveGraphConvolution.forward`` on the whole clip, so its softmax attention is taken over all T frames
+    (models/a_gcn/a_gcn.py:53-62) -- and is not reproduced by stepping, so ``forward`` in ``"clip"`` mode raises."""
 
     PADDING, STRIDED, ADAPTIVE = 4, True, True
+
+    def forward(self, input):
+        if self.hparams.forward_mode != "frame":
+            raise NotImplementedError(
+                "CoAGcn implements the continual per-step path only: the reference's clip forward attends over all T frames "
+                "(models/a_gcn/a_gcn.py:53-62), which stepping does not reproduce; construct with forward_mode='frame'")
+        return super().forward(input)
 
 
 class CoSTr(CoModelBase):

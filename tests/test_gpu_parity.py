@@ -4,8 +4,9 @@ against the CPU oracle and the committed golden fixtures.
 Tolerances.  The north star asks for max |dlogit| <= 1e-3 with identical argmax at the reference's
 random init (logit magnitude <= 16).  State is split-bf16 (hi + lo, ~17 mantissa bits) and the dense
 contractions are 3-product bf16 MMAs with fp32 accumulation, so block outputs are compared with a
-relative bound of 1e-4 of the tensor's magnitude; the randomised-BN variant has logits up to ~100
-and its absolute logit bound is scaled by max|logit| / 16.  The emission schedule (which block
+relative bound of 1e-4 of the tensor's magnitude; at the reference init the logit bound is
+the north star's absolute 1e-3 for every model; the randomised-BN stress variant has logits up to ~100 and its
+bound is scaled by max|logit| / 16 (the unscaled figures are printed and kept in profiles/r2_parity_report.txt).  The emission schedule (which block
 fires on which frame) is integer bookkeeping and must match bit for bit.
 """
 import numpy as np
@@ -105,8 +106,10 @@ def test_model_forward_steps_vs_reference(golden, cls, arch_fn, tag, rnd, path):
     out = out.cpu()
     sfx = "_rnd" if rnd else ""
     want = torch.from_numpy(golden[tag][f"{tag}_co_logits{sfx}"])  # made with the reference's blocks
-    scale = max(1.0, float(want.abs().max()) / 16.0)
+    # reference init: the north-star gate in absolute terms; randomised-BN stress variant: relative to max|logit| / 16
+    scale = max(1.0, float(want.abs().max()) / 16.0) if rnd else 1.0
     err = float((out - want).abs().max())
+    print(f"\n[parity] {tag} {'randomised' if rnd else 'reference-init'} path={path}: max|d|={err:.3e} max|logit|={float(want.abs().max()):.2f}")
     assert err <= 1e-3 * scale, (tag, rnd, path, err, float(want.abs().max()))
     assert torch.equal(out.argmax(1), want.argmax(1))
     assert torch.equal(torch.topk(out, 3).indices, torch.topk(want, 3).indices)
@@ -345,8 +348,9 @@ def test_coa_gcn_forward_steps_vs_reference(golden, rnd, path):
     assert out is not None and tuple(out.shape) == (2, 60)
     out = out.cpu()
     want = torch.from_numpy(golden["coa_gcn"]["coa_gcn_co_logits" + ("_rnd" if rnd else "")])
-    scale = max(1.0, float(want.abs().max()) / 16.0)
+    scale = max(1.0, float(want.abs().max()) / 16.0) if rnd else 1.0
     err = float((out - want).abs().max())
+    print(f"\n[parity] {'randomised' if rnd else 'reference-init'} path={path}: max|d|={err:.3e} max|logit|={float(want.abs().max()):.2f}")
     assert err <= 1e-3 * scale, (rnd, path, err, float(want.abs().max()))
     assert torch.equal(out.argmax(1), want.argmax(1))
 
@@ -427,7 +431,7 @@ def test_full_size_4096_streams_replica_property(golden, cls, arch_fn, tag):
     base = weights.make_input((2, 3, 300, 25, 2), seed=11).to(DEV)
     small = m.forward_steps(base)
     want = torch.from_numpy(golden[tag][f"{tag}_co_logits"])
-    assert float((small.cpu() - want).abs().max()) <= 1e-3 * max(1.0, float(want.abs().max()) / 16.0)
+    assert float((small.cpu() - want).abs().max()) <= 1e-3
     reps = 2048
     big = m.forward_steps(base.unsqueeze(0).expand(reps, 2, 3, 300, 25, 2).reshape(2 * reps, 3, 300, 25, 2))
     assert m.device_error() == 0
@@ -487,8 +491,9 @@ def test_cos_tr_forward_steps_vs_reference(golden, rnd, path):
     assert out is not None and tuple(out.shape) == (2, 400)
     out = out.cpu()
     want = torch.from_numpy(golden["cos_tr"]["cos_tr_co_logits" + ("_rnd" if rnd else "")])
-    scale = max(1.0, float(want.abs().max()) / 16.0)
+    scale = max(1.0, float(want.abs().max()) / 16.0) if rnd else 1.0
     err = float((out - want).abs().max())
+    print(f"\n[parity] {'randomised' if rnd else 'reference-init'} path={path}: max|d|={err:.3e} max|logit|={float(want.abs().max()):.2f}")
     assert err <= 1e-3 * scale, (rnd, path, err, float(want.abs().max()))
     assert torch.equal(out.argmax(1), want.argmax(1))
     if path == "auto":
