@@ -27,18 +27,51 @@ import torch  # noqa: E402
 METRIC = "CoST-GCN NTU60 stream-frames/s"
 UNIT = "stream-frames/s"
 V, S, C_IN, CLASSES = 25, 2, 3, 60
-# algorithmic bytes per stream-frame (SURVEY.md section 8d / BASELINE.md section 3): state bytes moved
-# + input frame + logits per emission + pool running-sum minimum
-ALGO = {
-    "cost_gcn": {"state": 1.408e6, "io": 600 + 240 / 4 + 2048 / 4, "flops": 115.0e6, "warm": 297, "period": 4},
-    "cost_gcn_mod": {"state": 3.072e6, "io": 600 + 240 + 2048, "flops": 318.0e6, "warm": 300, "period": 1},
-    # CoA-GCN: same rings and schedule as CoST-GCN; FLOPs scaled by the paper's
-    # per-prediction costs, 0.30 G vs 0.27 G (figures/table-2.png)
-    "coa_gcn": {"state": 1.408e6, "io": 600 + 240 / 4 + 2048 / 4, "flops": 115.0e6 * 0.30 / 0.27, "warm": 297, "period": 4},
-    # CoS-TR on the 18-joint Kinetics skeleton (BASELINE configs[3]): CoST-GCN's rings
-    # scaled by 18/25 vertices; FLOPs from the paper's 0.16 G per prediction on Kinetics (figures/table-5.png)
-    "cos_tr": {"state": 1.408e6 * 18 / 25, "io": 432 + 1600 / 4 + 2048 / 4, "flops": 0.16e9 / 4 * 2, "warm": 297, "period": 4},
-}
+# warm frames to the first logits and frames per prediction of each workload
+SCHED = {"cost_gcn": (297, 4), "cost_gcn_mod": (300, 1), "coa_gcn": (297, 4), "cos_tr": (297, 4)}
+
+
+def stack_blocks(workload):
+    """(cin, cout, stride, has_residual, graph-conv kind) of the ten blocks (models/cost_gcn/cost_gcn.py:30-41,
+    models/cost_gcn_mod/cost_gcn_mod.py:29-40, models/coa_gcn/coa_gcn.py:17-46, models/cos_tr/cos_tr.py:24-41)."""
+    s = 1 if workload == "cost_gcn_mod" else 2
+    chans = [(C_IN, 64, 1), (64, 64, 1), (64, 64, 1), (64, 64, 1), (64, 128, s), (128, 128, 1), (128, 128, 1), (128, 256, s),
+             (256, 256, 1), (256, 256, 1)]
+    kind = {"coa_gcn": "adaptive"}.get(workload, "plain")
+    return [(ci, co, st, i > 0, "attention" if (workload == "cos_tr" and i >= 3) else kind) for i, (ci, co, st) in enumerate(chans)]
+
+
+def algorithmic_cost(workload, v=None):
+    """Algorithmic work per stream-frame, derived from the block table (minimal input-ring algorithm,
+    fp32 state, S = 2 skeletons): per executed block 1 ring-frame write, per emitting step 8 ring-frame reads and -- for
+    blocks with a residual -- a delay-line read + write; MACs of the reference math with stride-phase skipping
+    (models/base.py:260-270 graph conv, :307-334 temporal conv; models/a_gcn/a_gcn.py:48-69 embeddings + per-frame V x V
+    attention; models/s_tr/s_tr.py:134-231 qkv / 8-head attention / output conv).  Checked against the SURVEY totals in
+    tests/test_boundary_cpu.py.  Returns per-block lists as well (bytes, MACs, executions and emissions per frame)."""
+    v = V if v is None else v
+    rate, state, macs, per_block = 1.0, 0.0, 0.0, []
+    for cin, cout, stride, res, kind in stack_blocks(workload):
+        frame = v * cout * 4.0
+        r_in, r_out = rate, rate / stride
+        b_gcn, b_tcn = frame, 8 * frame + (2 * frame if res else 0.0)  # per gcn execution / per tcn emission, one skeleton
+        if kind == "attention":
+            dk, dv = cout // 4, cout
+            g = cin * (2 * dk + dv) * v + v * v * (dk + dv) + dv * dv * v
+        else:
+            g = 3 * cin * v * v + 3 * cin * cout * v + (cin * cout * v if cin != cout else 0)
+            if kind == "adaptive":
+                g += 6 * cin * (cout // 4) * v + 3 * v * v * (cout // 4)
+        t = 9 * cout * cout * v + (cin * cout * v if (res and (cin != cout or stride != 1)) else 0)
+        state += S * (r_in * b_gcn + r_out * b_tcn)
+        macs += S * (r_in * g + r_out * t)
+        per_block.append({"cin": cin, "cout": cout, "gcn_bytes": S * b_gcn, "tcn_bytes": S * b_tcn, "gcn_macs": S * g, "tcn_macs": S * t,
+                          "gcn_per_frame": r_in, "tcn_per_frame": r_out})
+        rate = r_out
+    warm, period = SCHED[workload]
+    io = C_IN * v * S * 4 + (CLASSES * 4 + 2048) / period  # input frame + logits and pool running-sum minimum per emission
+    return {"state": state, "io": io, "flops": 2.0 * macs, "warm": warm, "period": period, "blocks": per_block}
+
+
 NAMES = {"cost_gcn": "CoST-GCN", "cost_gcn_mod": "CoST-GCN*", "coa_gcn": "CoA-GCN", "cos_tr": "CoS-TR"}
 # workload -> V, classes, dataset, label (BASELINE configs[2] quotes CoA-GCN on NTU RGB+D 120, configs[3] CoS-TR on Kinetics)
 GEOMETRY = {"cos_tr": (18, 400, "dummy_kin", "Kinetics-400 skeleton"), "coa_gcn": (25, 120, "ntu120", "NTU RGB+D 120 joint stream")}
@@ -51,11 +84,30 @@ def set_geometry(workload):
     V, CLASSES, DATASET, DATA_LABEL = GEOMETRY.get(workload, (25, 60, "dummy_ntu", "NTU RGB+D 60 joint stream"))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 4096 streams (bytes), averaged over the launches listed in
-# profiles/r1n_ncu_full_main_summary.csv (ncu --set full of one full step; earlier capture with --cache-control none:
-# profiles/r1h_dram_bytes_per_launch.csv); None where no capture exists.
-NCU_TRAFFIC = {"tcn<64>": 552.0e6, "tcn<128>": 1115.0e6, "tcn<256>": 2256.0e6, "gcn<64>": 59.0e6, "gcn<128>": 158.0e6,
-               "gcn<256>": 387.0e6}
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "ncu_full_main_summary.csv")  # newest `ncu --set full` export of one full step
+
+
+def ncu_traffic(kernel_regex, streams):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels matching `kernel_regex`, averaged over the
+    launches in the committed ncu export (profiles/ncu_full_main_summary.csv, produced from an `ncu --set full` capture of
+    `bench.py --streams 4096` by profiles/ncu_export.py).  None when there is no capture for this kernel / stream count."""
+    import csv
+    import re
+
+    if streams != 4096 or not os.path.exists(NCU_SUMMARY):
+        return None
+    rows = list(csv.reader(open(NCU_SUMMARY)))
+    if len(rows) < 3:
+        return None
+    hdr, units = rows[0], rows[1]
+    try:
+        k, r, w = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(x[r]) * mult.get(units[r], 1.0) + float(x[w]) * mult.get(units[w], 1.0) for x in rows[2:]
+            if len(x) > max(k, r, w) and re.search(kernel_regex, x[k])]
+    return sum(vals) / len(vals) if vals else None
 
 
 def load_peaks():
@@ -68,7 +120,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  The sampler is started well before the timed
+    regions (spawning nvidia-smi next to a 40 ms region perturbs it) and every sample carries a host timestamp, so the
+    summary can be restricted to the samples that fell inside a timed window."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -78,7 +132,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -87,28 +141,36 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows):
+        """`windows`: list of (t0, t1) host times of the timed regions; falls back to all samples under load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        good = [(ts, r) for ts, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        # nvidia-smi prints a sample at the END of its interval: accept samples up to one period after a window
+        inside = [r for ts, r in good if any(t0 <= ts <= t1 + 0.06 for t0, t1 in windows)]
+        where = "timed regions"
+        if len(inside) < 3:
+            inside, where = [r for ts, r in good if windows and windows[0][0] - 1.0 <= ts <= windows[-1][1] + 0.06], "warm-up + timed regions"
+        if not inside:
+            inside, where = [r for _, r in good], "whole run"
+        sm = [float(r[1]) for r in inside]
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in inside if r[3].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in inside:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": statistics.median(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm), "sampled_over": where}
 
 
 def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
@@ -124,7 +186,7 @@ def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
     frames = [torch.rand(n_streams, C_IN, V, S) for _ in range(4)]
     per = []
     with torch.no_grad():
-        for t in range(ALGO[workload]["warm"] + warm_extra):
+        for t in range(SCHED[workload][0] + warm_extra):
             model.forward_step(frames[t % 4])
         model.trace = []
         t0 = time.perf_counter()
@@ -136,6 +198,10 @@ def cpu_port_rate(workload, n_streams, steps, warm_extra=0, threads=None):
     return n_streams * steps / dt, dt / steps * 1e3, statistics.median(per) * 1e3, torch.get_num_threads()
 
 
+def metric_name(workload):
+    return METRIC.replace("CoST-GCN", NAMES[workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU120" if CLASSES == 120 else "NTU60")
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -143,9 +209,9 @@ def run_reference(args, rank, world):
     config = make_config(args, world)
     rate, ms, p50, cores = cpu_port_rate(args.workload, n_sample, args.steps, warm_extra=args.warmup)
     sample = (f"{n_sample} concurrent streams per step (bounded sample of the {args.streams}-stream workload), steady state "
-              f"after {ALGO[args.workload]['warm']} warm frames, oracle/step.py eager torch fp32")
+              f"after {SCHED[args.workload][0]} warm frames, oracle/step.py eager torch fp32")
     line = {
-        "impl": "reference", "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU120" if CLASSES == 120 else "NTU60"), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.workload), "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "p50_ms_per_step": p50, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -155,16 +221,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def kernel_label(path, kname, cout, kblock, workload="cost_gcn"):
+def kernel_label(path, kname, cin, cout, kblock, workload, knobs):
     if path != "auto":
-        return f"k_{kname}_simt (layer {kblock + 1}, C={cout})"
+        return f"k_{kname}_simt (layer {kblock + 1}, C={cout})", None
+    if kname == "block":
+        return f"k_tc_block64 (layer {kblock + 1}; graph conv + temporal conv of the block step in one kernel)", r"k_tc_block64"
     if kname == "tcn":
-        return (f"k_tc_tcn<{cout}>" if cout == 64 else f"k_tc_tcn2<{cout}> (CTA pairs)") + f" (layer {kblock + 1})"
+        pair = cout >= 128
+        name = f"k_tc_tcn2<{cout}>" if pair else f"k_tc_tcn<{cout}>"
+        return name + (" (CTA pairs)" if pair else "") + f" (layer {kblock + 1})", rf"k_tc_tcn2?<{cout}>"
     if workload == "coa_gcn":
-        return f"k_tc_agcn C={cout} (layer {kblock + 1}; dense per-skeleton mix, attention kernel timed separately)"
+        return f"k_tc_agcn C={cout} (layer {kblock + 1}; dense per-skeleton mix, attention kernel timed separately)", None
     if workload == "cos_tr" and kblock >= 3:
-        return f"attention-unit output conv, k_tc_tcn with one tap, C={cout} (layer {kblock + 1}; qkv + attention timed separately)"
-    return f"k_tc_gcn<4> C={cout} (layer {kblock + 1})"
+        return f"attention-unit output conv, k_tc_tcn with one tap, C={cout} (layer {kblock + 1}; qkv + attention timed separately)", None
+    if cin < 64:
+        return f"k_gcn_small (layer {kblock + 1})", r"k_gcn_small"
+    if "gcnp" in knobs.get("graph_conv", {}).get(str(cout), ""):
+        return f"k_tc_gcnp<{cout}> (layer {kblock + 1}; pre-mix, A operand in TMEM)", rf"k_tc_gcnp<{cout},"
+    return f"k_tc_gcn C={cout} (layer {kblock + 1}; GEMM-then-mix)", r"k_tc_gcn<"
 
 
 def make_config(args, world):
@@ -172,7 +246,9 @@ def make_config(args, world):
         "workload": f"{NAMES[args.workload]} {DATA_LABEL}, per-step forward_step, {args.streams} concurrent streams per GPU, "
                     f"random-init weights, synthetic U[0,1) frames (N,C=3,V={V},S=2)",
         "model_variant": args.workload, "streams_per_gpu": args.streams, "streams_total": args.streams * world,
-        "V": V, "S": S, "classes": CLASSES, "sharding": f"streams sharded over {world} rank(s), logits all-gathered on emitting steps",
+        "V": V, "S": S, "classes": CLASSES,
+        "sharding": f"streams sharded over {world} rank(s); on emitting steps the logits are all-gathered (NCCL) on a side stream into "
+                    f"pre-allocated device buffers; every rank reads back its own shard's logits in the e2e pass",
         "l2": "per-step state traffic is GBs (>> 126 MB L2) and 8 distinct input frames are cycled, so no L2 flush is needed",
     }
 
@@ -184,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    algo = ALGO[args.workload]
+    algo = algorithmic_cost(args.workload)
     cls = {"cost_gcn": cs.CoStGcn, "cost_gcn_mod": cs.CoStGcnMod, "coa_gcn": cs.CoAGcn, "cos_tr": cs.CoSTr}[args.workload]
     torch.manual_seed(0)
     model = cls({"dataset_name": DATASET, "forward_mode": "frame", "kernel_path": args.kernel_path})
@@ -193,6 +269,11 @@ def run_ours(args, rank, world, local_rank):
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     host_frames = [torch.rand((n_local, C_IN, V, S), generator=gen).pin_memory() for _ in range(8)]
     dev_frames = [f.to(dev) for f in host_frames]
+    gather = cs.LogitGather(n_total, CLASSES, dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # long before the first timed region
 
     def barrier():
         if world > 1:
@@ -201,11 +282,16 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident(t):
         out = model.forward_step(dev_frames[t % 8])
-        if out is not None and world > 1:
-            out = cs.all_gather_logits(out, n_total)
+        if out is not None:
+            gather.launch(out)  # side stream: the next step does not wait for the collective
         return out
 
-    # state warm-up to steady state (every ring full, logits emitting), then W untimed steps
+    def join_side_stream():
+        r = gather.result()  # current stream waits for the newest gather: it is inside whatever is being timed
+        return r
+
+    # state warm-up to steady state (every ring full, logits emitting), W untimed steps, then steady running for at least
+    # --prewarm-s seconds so that clocks and power state have settled before anything is timed
     t = 0
     for _ in range(algo["warm"]):
         step_resident(t)
@@ -213,48 +299,36 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step_resident(t)
         t += 1
+    torch.cuda.synchronize()
+    t_pre = time.time()
+    while time.time() - t_pre < args.prewarm_s:
+        for _ in range(16):
+            step_resident(t)
+            t += 1
+        torch.cuda.synchronize()
     assert model.device_error() == 0, hex(model.device_error())
+    windows = []
 
     # ---- timed region 1: inputs resident in HBM ---------------------------------------------
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     launches0 = model.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ncu = os.environ.get("COSK_NCU") == "1"  # profile only the timed steps: ncu --profile-from-start off
     if ncu:
         torch.cuda.cudart().cudaProfilerStart()
+    w0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step_resident(t)
         t += 1
+    join_side_stream()
     ev1.record()
     barrier()
+    windows.append((w0, time.time()))
     if ncu:
         torch.cuda.cudart().cudaProfilerStop()
     elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     launches = model.launch_count() - launches0
-    # ---- timed region 1b: the same K steps again with the library's per-kernel CUDA events on the
-    # launching stream (an event between two kernels serialises them, so this pass is kept out of `value`)
-    model.profile(True)
-    for _ in range(args.steps):
-        step_resident(t)
-        t += 1
-    barrier()
-    prof = {}
-    for kind, name in ((0, "input"), (1, "gcn"), (2, "tcn"), (3, "head"), (4, "attn")):
-        ms, n = model.profile_read(kind)
-        prof[name] = {"ms": ms, "launches": n}
-    per_block = []
-    for b in range(10):
-        g_ms, g_n = model.profile_read(1, b)
-        t_ms, t_n = model.profile_read(2, b)
-        per_block.append({"gcn_ms": g_ms, "gcn_n": g_n, "tcn_ms": t_ms, "tcn_n": t_n})
-        if args.workload in ("coa_gcn", "cos_tr"):
-            per_block[-1]["attn_ms"], per_block[-1]["attn_n"] = model.profile_read(4, b)
-    model.profile(False)
     if world > 1:
         tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -262,33 +336,59 @@ def run_ours(args, rank, world, local_rank):
     value = n_total * args.steps / (elapsed_ms * 1e-3)
 
     # ---- timed region 2: end to end through the public API with HOST buffers ------------------
-    stage = torch.empty((n_local, C_IN, V, S), device=dev)
-    host_out = torch.empty((n_total if world > 1 else n_local, CLASSES)).pin_memory()
+    # every step: pinned host frame -> device, forward_step, and on emitting steps the rank's logits -> pinned host
+    # (the all-gather runs beside it on the side stream, as in region 1)
+    stage = [torch.empty((n_local, C_IN, V, S), device=dev) for _ in range(2)]
+    host_out = torch.empty((n_local, CLASSES)).pin_memory()
     h2d = n_local * C_IN * V * S * 4
     d2h_total = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
     e0.record()
-    for _ in range(args.steps):
-        stage.copy_(host_frames[t % 8], non_blocking=True)
-        out = model.forward_step(stage)
+    for i in range(args.steps):
+        buf = stage[i & 1]
+        buf.copy_(host_frames[t % 8], non_blocking=True)
+        out = model.forward_step(buf)
         if out is not None:
-            if world > 1:
-                out = cs.all_gather_logits(out, n_total)
+            gather.launch(out)
             host_out.copy_(out, non_blocking=True)
             d2h_total += out.numel() * 4
         t += 1
+    join_side_stream()
     e1.record()
     barrier()
+    windows.append((w0, time.time()))
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
     e2e_value = n_total * args.steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop(windows) if rank == 0 else None
+
+    # ---- the same K steps again with the library's per-kernel CUDA events on the launching stream (an event between
+    # two kernels serialises them, so this pass is kept out of `value`) ----------------------------------------------
+    model.profile(True)
+    for _ in range(args.steps):
+        step_resident(t)
+        t += 1
+    barrier()
+    prof = {}
+    for kind, name in ((0, "input"), (1, "gcn"), (2, "tcn"), (3, "head"), (4, "attn"), (5, "block")):
+        ms, n = model.profile_read(kind)
+        prof[name] = {"ms": ms, "launches": n}
+    per_block = []
+    for b in range(10):
+        g_ms, g_n = model.profile_read(1, b)
+        t_ms, t_n = model.profile_read(2, b)
+        f_ms, f_n = model.profile_read(5, b)  # fused block step: one launch = one graph conv + one temporal conv
+        per_block.append({"gcn_ms": g_ms, "gcn_n": g_n, "tcn_ms": t_ms, "tcn_n": t_n, "block_ms": f_ms, "block_n": f_n})
+        if args.workload in ("coa_gcn", "cos_tr"):
+            per_block[-1]["attn_ms"], per_block[-1]["attn_n"] = model.profile_read(4, b)
+    model.profile(False)
 
     # ---- per-step latency (events per step, separate pass) -----------------------------------
-    lat = []
     n_lat = min(args.steps, 200)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_lat + 1)]
     barrier()
@@ -304,34 +404,43 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peaks = load_peaks()
-    # dominant kernel: the (kind, block) with the largest summed device time
-    best = max(((pb["tcn_ms"], "tcn", i) for i, pb in enumerate(per_block)), default=(0, "tcn", 9))
-    bg = max(((pb["gcn_ms"], "gcn", i) for i, pb in enumerate(per_block)), default=(0, "gcn", 9))
-    if bg[0] > best[0]:
-        best = bg
-    _, kname, kblock = best
-    pb = per_block[kblock]
-    k_ms, k_n = (pb["tcn_ms"], pb["tcn_n"]) if kname == "tcn" else (pb["gcn_ms"], pb["gcn_n"])
-    cout = [64, 64, 64, 64, 128, 128, 128, 256, 256, 256][kblock]
+    knobs = model.knobs()
     tokens = n_local * S * V
-    # algorithmic frames of (tokens x C x 4 B) per launch: temporal conv = 8 ring reads +
-    # 1 delayed-residual read + 1 output write; graph conv = 1 ring write
-    frames_moved = 10 if kname == "tcn" else 1
-    k_bytes = frames_moved * tokens * cout * 4.0
+    blocks = algo["blocks"]
+    # per block: the north star's own unit.  Algorithmic bytes / 1-product FLOPs of the launches timed in the profiled
+    # pass over their summed device time (graph conv + attention half + temporal conv of that block).
+    per_block_roofline = []
+    for i, (pb, ab) in enumerate(zip(per_block, blocks)):
+        ms = pb["gcn_ms"] + pb["tcn_ms"] + pb.get("attn_ms", 0.0) + pb["block_ms"]
+        n_g, n_t = pb["gcn_n"] + pb["block_n"], pb["tcn_n"] + pb["block_n"]  # timed pass is steady state: a fused launch does both
+        by = n_local * (n_g * ab["gcn_bytes"] + n_t * ab["tcn_bytes"])
+        fl = 2.0 * n_local * (n_g * ab["gcn_macs"] + n_t * ab["tcn_macs"])
+        per_block_roofline.append({
+            "layer": i + 1, "cin": ab["cin"], "cout": ab["cout"], "ms_per_block_step": ms / max(n_g, 1),
+            "kernels": "fused" if pb["block_n"] else "gcn + tcn",
+            "hbm_frac": by / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"] if ms > 0 else None,
+            "tensor_frac_1product": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"] if ms > 0 else None,
+            "tensor_frac_issued_3product": 3 * fl * (128.0 / 125.0 if V == 25 else 128.0 / 126.0) / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"] if ms > 0 else None,
+        })
+    # dominant kernel: the (kind, block) with the largest summed device time
+    best = max(((pb[k + "_ms"], k, i) for i, pb in enumerate(per_block) for k in ("tcn", "gcn", "block")), default=(0, "tcn", 9))
+    _, kname, kblock = best
+    pb, ab = per_block[kblock], blocks[kblock]
+    k_ms, k_n = pb[kname + "_ms"], pb[kname + "_n"]
+    cin, cout = ab["cin"], ab["cout"]
+    # algorithmic bytes per launch: temporal conv = 8 ring-frame reads + delayed-residual read +
+    # output write (the delay-line read + write of SURVEY 8d); graph conv = 1 ring-frame write; fused block step = both
+    k_bytes = n_local * {"tcn": ab["tcn_bytes"], "gcn": ab["gcn_bytes"], "block": ab["tcn_bytes"] + ab["gcn_bytes"]}[kname]
     k_avg_ms = k_ms / max(k_n, 1)
     achieved = k_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
-    # tensor side of the same kernel: credited = 1-product FLOPs of the reference math; issued = the three
-    # split-precision products actually executed on the 128-row tiles (125 valid rows per tile)
-    cin = [C_IN, 64, 64, 64, 64, 128, 128, 128, 256, 256][kblock]
-    res_k = cin if kblock in (4, 7) else 0
-    k_macs = tokens * cout * ((9 * cout + res_k) if kname == "tcn" else (3 * cin + (cin if cin != cout else 0)))
-    k_tf_credit = 2.0 * k_macs / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
-    issued_k = (9 * cout + res_k) if kname == "tcn" else 4 * cin
-    k_tf_issued = 3 * 2.0 * (tokens * 128.0 / 125.0) * cout * issued_k / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC.get(f"{kname}<{cout}>") if n_local == 4096 and V == 25 and not (args.workload == "coa_gcn" and kname == "gcn") else None
+    k_flops = 2.0 * n_local * {"tcn": ab["tcn_macs"], "gcn": ab["gcn_macs"], "block": ab["tcn_macs"] + ab["gcn_macs"]}[kname]
+    k_tf_credit = k_flops / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
+    k_tf_issued = 3 * k_flops * (128.0 / 125.0) / (k_avg_ms * 1e-3) / 1e12 if k_avg_ms > 0 else 0.0
+    label, regex = kernel_label(args.kernel_path, kname, cin, cout, kblock, args.workload, knobs)
+    traffic = ncu_traffic(regex, n_local) if (regex and V == 25) else None
     step_bytes = algo["state"] + algo["io"]
     line = {
-        "metric": METRIC.replace("CoST-GCN", NAMES[args.workload]).replace("NTU60", "Kinetics" if V == 18 else "NTU120" if CLASSES == 120 else "NTU60"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3 (split-bf16 operands, f32 accumulate)" if args.kernel_path == "auto" else "f32",
         "data": "synthetic", "config": make_config(args, world),
@@ -341,9 +450,10 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "roofline": {
-            "bound": "hbm", "kernel": kernel_label(args.kernel_path, kname, cout, kblock, args.workload),
+            "bound": "hbm", "kernel": label,
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": traffic, "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
+            "traffic": traffic, "traffic_source": os.path.relpath(NCU_SUMMARY, ROOT) if traffic else None,
+            "algorithmic_bytes_per_launch": k_bytes, "avg_launch_ms": k_avg_ms, "launches_timed": k_n,
             "peak_source": peaks["source"],
             "tensor": {"credited_tflops_1product": k_tf_credit, "issued_tflops_3product": k_tf_issued, "peak_tflops": peaks["bf16_tflops"],
                        "frac_credited": k_tf_credit / peaks["bf16_tflops"], "frac_issued": k_tf_issued / peaks["bf16_tflops"]},
@@ -354,10 +464,12 @@ def run_ours(args, rank, world, local_rank):
             "algorithmic_bytes_per_stream_frame": step_bytes, "algorithmic_flops_per_stream_frame": algo["flops"],
             "note": "1-product FLOPs and minimal state traffic; the 3 split-precision products and unfused inter-kernel traffic are not credited",
         },
+        "per_block_roofline": per_block_roofline,
         "kernel_time_ms": {k: v for k, v in prof.items()},
         "kernel_time_per_block_ms": per_block,
         "state_bytes": model.state_bytes(),
         "tensor_core_blocks": model.tensor_core_blocks(),
+        "kernel_knobs": knobs,
     }
     if world == 1 and not args.no_cpu_baseline:
         rate, ms, p50, cores = cpu_port_rate(args.workload, args.ref_streams, 40)
@@ -375,10 +487,11 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cost_gcn", choices=list(ALGO))
+    ap.add_argument("--workload", default="cost_gcn", choices=list(SCHED))
     ap.add_argument("--streams", type=int, default=4096, help="concurrent streams per GPU")
     ap.add_argument("--ref-streams", type=int, default=64, help="streams per step of the CPU sample")
     ap.add_argument("--kernel-path", default="auto", choices=["auto", "simt"])
+    ap.add_argument("--prewarm-s", type=float, default=1.5, help="seconds of steady stepping before the first timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     set_geometry(args.workload)

@@ -17,6 +17,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_gcnp.cuh"
+#include "tc_block.cuh"
 
 using namespace cosk;
 
@@ -79,6 +80,12 @@ struct BlockW {
   bool tc_gcn = false, tc_tcn = false;
   // pre-mix graph conv (k_tc_gcnp): weights [2*cout rows (hi, lo)][gcnp_parts*cin], partition-major K
   bool tc_gcnp = false, gcnp_stacked = false, gcnp_unit_diag = false;
+  bool gcnp_ready = false;  // weights of the pre-mix form are uploaded (k_tc_gcnp and the fused block kernel use them)
+  bool fuse = false;        // this block's step runs as ONE kernel (k_tc_block64)
+  CUtensorMap map_tcn_w_full;  // temporal-conv weights with a 2*cout-row box: hi and lo rows in one stacked slab
+  __nv_bfloat16 *d_blk_gw16 = nullptr;  // graph-conv weights of the fused kernel: [2*cout rows][blk_parts*cin], K-blocks in mix-slot order
+  CUtensorMap map_blk_gw;
+  int blk_parts = 4;
   int gcnp_parts = 3;
   __nv_bfloat16 *d_gcnp_w16 = nullptr;
   CUtensorMap map_gcnp_w;
@@ -118,8 +125,10 @@ struct cosk_model {
   int agcn_tc = 1;  // adaptive graph conv on the tcgen05 kernels (COSK_AGCN_TC=0: fp32 CUDA-core kernels)
   int tcn_identity_mma = 1;  // narrow temporal convs: identity residual as a K-block of the GEMM (COSK_TCN_IDENTITY_MMA=0: epilogue add)
   int pdl = 1;  // programmatic dependent launch between the kernels of a step: +16 % at 256 streams, +4 % at 1024, neutral at 4096 (COSK_PDL=0 disables)
-  int gcn_premix = 7;  // which plain graph-conv widths run on the pre-mix / A-in-TMEM kernel k_tc_gcnp (bit 0: 64, bit 1: 128,
-                       // bit 2: 256 output channels); the rest stays on k_tc_gcn (COSK_GCN_PREMIX)
+  int gcn_premix = 0;  // which plain graph-conv widths run on the standalone pre-mix / A-in-TMEM kernel k_tc_gcnp (bit 0: 64, bit 1: 128,
+                       // bit 2: 256 output channels); the rest stays on k_tc_gcn (COSK_GCN_PREMIX).  Off: measured slower standalone
+                       // (profiles/r2a_gcnp_ab.txt) -- its CUDA-core mix only pays off hidden under the temporal conv's HBM stream
+  int fuse_block = 1;  // 64 -> 64 identity-residual blocks: graph conv + temporal conv in one kernel per step (COSK_FUSE_BLOCK=0: two kernels)
   int gcnp_identity_mma = 3;  // widths whose identity gcn_residual rides in the pre-mix GEMM as a 4th part (same bits; others: epilogue add)
   int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
@@ -419,8 +428,9 @@ int prepare(cosk_model *m) {
       for (int p = 1; p < 3; ++p)
         for (int w = 0; w < V; ++w) part_max = std::max(part_max, ptr[p * V + w + 1] - ptr[p * V + w]);
       const int wbit = bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4;
-      b.tc_gcnp = b.tc_gcn && !adaptive && !attention && tc_width(bc.cout) && (m->gcn_premix & wbit) && part_max <= kPartSrcMax;
-      if (b.tc_gcnp) {
+      b.gcnp_ready = b.tc_gcn && !adaptive && !attention && tc_width(bc.cout) && part_max <= kPartSrcMax;
+      b.tc_gcnp = b.gcnp_ready && (m->gcn_premix & wbit);
+      if (b.gcnp_ready) {
         const bool ident_mma = !res_conv && (m->gcnp_identity_mma & wbit);
         const int P = b.gcnp_parts = (res_conv || ident_mma) ? 4 : 3;
         const int K = P * bc.cin;
@@ -555,6 +565,33 @@ int prepare(cosk_model *m) {
         return rc;
       if ((rc = make_map(m, &b.map_tcn_w_half, b.d_tcn_w16, (uint64_t)(Kt + Kr), (uint64_t)2 * bc.cout, (uint32_t)bc.cout / 2)))
         return rc;
+      if (bc.cout <= 128 &&
+          (rc = make_map(m, &b.map_tcn_w_full, b.d_tcn_w16, (uint64_t)(Kt + Kr), (uint64_t)2 * bc.cout, (uint32_t)(2 * bc.cout))))
+        return rc;
+    }
+    // one kernel per block step: 64 -> 64 blocks with the identity residual riding in both GEMMs
+    b.fuse = m->fuse_block && b.gcnp_ready && bc.cin == 64 && bc.cout == 64 && bc.stride == 1 &&
+             bc.res_kind == COSK_RES_IDENTITY && b.tc_tcn && b.tcn_res_kblock && bc.gconv == COSK_GCONV_PLAIN;
+    if (b.fuse) {
+      // K-blocks in the order the mix warps fill their slots: the plain input rows (identity gcn_residual; plus W_0 when every
+      // self link is exactly 1, so that x and 1*x share one part), [W_0 on a0*x], W_1, W_2
+      const int P = b.blk_parts = b.gcnp_unit_diag ? 3 : 4;
+      const int K = P * bc.cin;
+      std::vector<float> w((size_t)bc.cout * K, 0.f);
+      for (int o = 0; o < bc.cout; ++o) {
+        float *row = &w[(size_t)o * K];
+        const float *src = &b.gcn_w[(size_t)o * Kg];
+        row[o] = 1.0f;  // identity gcn_residual (cin == cout)
+        if (b.gcnp_unit_diag) {
+          for (int k = 0; k < bc.cin; ++k) row[k] += src[k];
+          memcpy(row + bc.cin, src + bc.cin, sizeof(float) * 2 * bc.cin);
+        } else {
+          memcpy(row + bc.cin, src, sizeof(float) * 3 * bc.cin);
+        }
+      }
+      std::vector<uint16_t> s16 = split_rows(w, bc.cout, K);
+      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_blk_gw16), s16.data(), s16.size()))) return rc;
+      if ((rc = make_map(m, &b.map_blk_gw, b.d_blk_gw16, (uint64_t)K, (uint64_t)2 * bc.cout, (uint32_t)(2 * bc.cout)))) return rc;
     }
   }
   m->prepared = true;
@@ -685,6 +722,7 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcnp<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, true>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnp<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnp<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<256, false>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_block64, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBlockCfg::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn_gcn<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           std::max(TcTcnCfg<64>::kSmemBytes, TcGcnCfg<4, 1>::kSmemBytes)));
   CK(cudaFuncSetAttribute(k_tc_tcn2_gcn<128, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -745,6 +783,7 @@ TcGcnpArgs make_gcnp_args(cosk_model *m, int i, const ActBuf &in, int in_slot, i
   a.mix_src = b.d_mix_src;
   a.mix_val = b.d_mix_val;
   a.unit_diag = b.gcnp_unit_diag ? 1 : 0;
+  a.trace = m->d_trace;
   a.epi.bias = b.d_gcn_b;
   const bool epi_res = b.gcnp_parts == 3;  // identity gcn_residual added by the epilogue from the input rows
   a.epi.r_hi = epi_res ? in.hi(in_slot) : nullptr;
@@ -802,7 +841,7 @@ bool can_merge(const cosk_model *m, int i) {
   if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.blocks[i + 1].gconv != COSK_GCONV_PLAIN) return false;
   const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
   const int c = m->cfg.blocks[i].cout;
-  if (!b.tc_tcn || !nb.tc_gcn || nb.tc_gcnp || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
+  if (!b.tc_tcn || !nb.tc_gcn || nb.tc_gcnp || nb.fuse || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
   if (m->n_tiles < m->merge_min_tiles) return false;
   if (c == 64) return m->gcn_single_stage && !(m->pair_mask & 1);
   if (c == 128) return (m->pair_mask & 2) != 0;
@@ -1210,6 +1249,49 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
   return COSK_OK;
 }
 
+// Graph conv + temporal conv of a 64 -> 64 block as one launch (k_tc_block64).  `fire`: the temporal conv emits on this step.
+int run_block64(cosk_model *m, int i, const ActBuf &in, int in_slot, long long n, bool fire, int res_slot, int out_slot, cudaStream_t s) {
+  BlockW &b = m->blk[i];
+  int rc = prof_mark(m, 5, i, s);
+  if (rc) return rc;
+  TcBlockArgs a;
+  a.tm_x = in.map;
+  a.tm_ring = b.ring.map;
+  a.tm_gw = b.map_blk_gw;
+  a.tm_tw = b.map_tcn_w_full;
+  a.n_parts = b.blk_parts;
+  a.x_row = (int)in.row_hi(in_slot);
+  a.res_row = fire ? (int)in.row_hi(res_slot) : 0;
+  for (int k = 0; k < kTaps - 1; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
+  a.t_alloc = (int)m->t_alloc;
+  a.with_tcn = fire ? 1 : 0;
+  a.V = m->cfg.vertices;
+  a.n_tiles = m->n_tiles;
+  a.tile_tokens = m->tile_tokens;
+  a.n_tokens = m->n_tokens;
+  a.mix_ptr = b.d_mix_ptr;
+  a.mix_src = b.d_mix_src;
+  a.mix_val = b.d_mix_val;
+  a.gbias = b.d_gcn_b;
+  const int ring_slot = (int)(n % kRingSlots);
+  a.g_hi = b.ring.hi(ring_slot);
+  a.g_lo = b.ring.lo(ring_slot);
+  a.cs_g = b.ring.cs;
+  a.tepi.bias = b.d_tcn_b;
+  a.tepi.r_hi = nullptr;  // the delayed identity residual is a K-block of the temporal GEMM
+  a.tepi.r_lo = nullptr;
+  a.tepi.cs_r = 0;
+  a.tepi.y_hi = b.out.hi(out_slot);
+  a.tepi.y_lo = b.out.lo(out_slot);
+  a.tepi.cs_out = b.out.cs;
+  a.trace = m->d_trace;
+  a.dbg = m->d_dbg;
+  const int grid = m->n_tiles < m->num_sms ? m->n_tiles : m->num_sms;
+  CK(launch_k(m, k_tc_block64, dim3(grid), dim3(512), TcBlockCfg::kSmemBytes, s, a));
+  m->launches++;
+  return COSK_OK;
+}
+
 // ---- the integer schedule (shared by the device path and cosk_simulate_schedule) -------------------
 // co.Conv2d step semantics: the n-th input (0-based) of a 9-tap temporal conv with padding p and
 // stride s produces an output iff n >= 8 - p and (n - (8 - p)) % s == 0   (SURVEY.md section 3.3).
@@ -1245,10 +1327,17 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const cosk_block_cfg &bc = c.blocks[i];
     const long long n = b.n_in;  // index of this input == index of the predecessor's emission
     const int in_slot = (int)(n % kOutSlots);
-    if (!gcn_done && (rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) return rc;
-    gcn_done = false;
     const bool fire = tcn_fires(n, c.padding, bc.stride);
-    if (fire) {
+    const bool fused = b.fuse && !gcn_done && in->has_map;
+    if (fused) {
+      const int res_slot = fire ? (int)((n - kResDelay) % kOutSlots) : 0;
+      if ((rc = run_block64(m, i, *in, in_slot, n, fire, res_slot, (int)(b.n_out % kOutSlots), s))) return rc;
+      if (fire) b.n_out++;
+    } else if (!gcn_done && (rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) {
+      return rc;
+    }
+    gcn_done = false;
+    if (fire && !fused) {
       const int res_slot = (int)((n - kResDelay) % kOutSlots);  // n >= first >= 4
       const int out_slot = (int)(b.n_out % kOutSlots);
       if (can_merge(m, i)) {
@@ -1354,6 +1443,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_TCN_PAIR")) m->pair_mask = atoi(e);
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
   if (const char *e = getenv("COSK_GCN_PREMIX")) m->gcn_premix = atoi(e);
+  if (const char *e = getenv("COSK_FUSE_BLOCK")) m->fuse_block = atoi(e);
   if (const char *e = getenv("COSK_GCNP_IDENTITY_MMA")) m->gcnp_identity_mma = atoi(e);
   if (const char *e = getenv("COSK_GCNP_STACKED")) m->gcnp_stacked = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
@@ -1425,6 +1515,7 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_adj);
     dfree(b.d_gcn_w16);
     dfree(b.d_gcnp_w16);
+    dfree(b.d_blk_gw16);
     dfree(b.d_tcn_w16);
     dfree(b.d_att_w16);
     dfree(b.d_sa_scale);
@@ -1660,6 +1751,62 @@ int64_t cosk_launch_count(const cosk_model *m) { return m ? m->launches : 0; }
 int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block) {
   if (!m || block < 0 || block >= m->cfg.n_blocks) return COSK_ERR_ARG;
   return ((m->blk[block].tc_gcn || m->blk[block].tc_sa_out) ? 1 : 0) | (m->blk[block].tc_tcn ? 2 : 0);
+}
+
+int cosk_describe(const cosk_model *m, char *buf, size_t n) {
+  if (!m || !buf || n < 2) return COSK_ERR_ARG;
+  std::string o = "{";
+  char t[1024];
+  snprintf(t, sizeof t,
+           "\"version\": \"%s\", \"path\": \"%s\", \"pdl\": %d, \"tcn_pair_mask\": %d, \"tcn_reverse\": %d, \"tcn_identity_mma\": %d, "
+           "\"fuse_block\": %d, \"gcn_premix\": %d, \"gcnp_identity_mma\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
+           "\"sa_fused\": %d, \"attn_tc\": %d, \"agcn_tc\": %d, \"trace\": %d, ",
+           cosk_version(), m->cfg.path == COSK_PATH_AUTO ? "auto" : "simt", m->pdl, m->pair_mask, m->tcn_reverse, m->tcn_identity_mma,
+           m->fuse_block, m->gcn_premix, m->gcnp_identity_mma, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
+           m->d_trace ? 1 : 0);
+  o += t;
+  o += "\"blocks\": [";
+  std::string by_width = "";
+  for (int i = 0; i < m->cfg.n_blocks; ++i) {
+    const cosk_block_cfg &bc = m->cfg.blocks[i];
+    const BlockW &b = m->blk[i];
+    std::string g, tc;
+    if (bc.gconv == COSK_GCONV_ATTENTION) g = b.tc_sa_fused ? "k_tc_sa" : (b.tc_sa_qkv ? "k_tc_tcn(qkv)+k_sa_attn" : "k_sa_qkv+k_sa_attn");
+    else if (bc.gconv == COSK_GCONV_ADAPTIVE) g = b.tc_gcn ? (b.tc_attn ? "k_tc_attn+k_tc_agcn" : "k_agcn_attn+k_tc_agcn") : "k_agcn_attn+k_gcn_simt";
+    else if (b.tc_gcnp) {
+      snprintf(t, sizeof t, "k_tc_gcnp<%d,%s> P=%d", bc.cout, b.gcnp_stacked ? "stacked" : "3-product", b.gcnp_parts);
+      g = t;
+    } else if (b.tc_gcn) {
+      snprintf(t, sizeof t, "k_tc_gcn<%d> GEMM-then-mix", b.gcn_parts);
+      g = t;
+    } else g = (m->cfg.path == COSK_PATH_AUTO && bc.cin <= 8) ? "k_gcn_small" : "k_gcn_simt";
+    if (b.tc_tcn) {
+      const bool pair = m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4);
+      snprintf(t, sizeof t, "%s<%d>", pair ? "k_tc_tcn2" : "k_tc_tcn", bc.cout);
+      tc = t;
+    } else tc = "k_tcn_simt";
+    if (b.fuse) {
+      snprintf(t, sizeof t, "%s{\"block\": \"k_tc_block64 (graph conv + temporal conv in one kernel)\"}", i ? ", " : "");
+      o += t;
+      continue;
+    }
+    snprintf(t, sizeof t, "%s{\"gcn\": \"%s\", \"tcn\": \"%s\"}", i ? ", " : "", g.c_str(), tc.c_str());
+    o += t;
+  }
+  o += "], \"graph_conv\": {";
+  bool firstw = true;
+  for (int w : {64, 128, 256})
+    for (int i = 0; i < m->cfg.n_blocks; ++i)
+      if (m->cfg.blocks[i].cout == w && m->cfg.blocks[i].cin >= 64 && m->cfg.blocks[i].gconv == COSK_GCONV_PLAIN) {
+        snprintf(t, sizeof t, "%s\"%d\": \"%s\"", firstw ? "" : ", ", w, m->blk[i].tc_gcnp ? "gcnp" : m->blk[i].tc_gcn ? "gcn" : "simt");
+        o += t;
+        firstw = false;
+        break;
+      }
+  o += "}}";
+  if (o.size() + 1 > n) return COSK_ERR_ARG;
+  memcpy(buf, o.c_str(), o.size() + 1);
+  return COSK_OK;
 }
 
 int cosk_device_error(cosk_model *m, uint32_t *code) {

@@ -44,6 +44,10 @@ struct TcGcnpArgs {
   const float *mix_val;
   int unit_diag;  // 1: every self-link coefficient is exactly 1, so part 0 is a copy of the input rows
   EpiArgs epi;    // r_hi / r_lo = input rows when the identity gcn_residual is added by the epilogue (n_parts == 3)
+  unsigned long long *trace;  // optional phase timers of CTA 0 (COSK_TRACE=1), SM clock cycles: [32..37] mix warp {wait input
+                              // K-block, compute, wait A slot, store + signal, total, slots}; [40..44] MMA thread {wait accumulator,
+                              // wait A slot, wait weights, issue, total}; [48..50] epilogue warp {wait accumulator, work, total};
+                              // [52..54] producer {wait input stage, wait weight stage, total}
   unsigned int *dbg;
 };
 
@@ -149,19 +153,26 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
     if (lane == 0) {
       PipeState px, pw;
       bool ok = true;
+      const bool tr = a.trace != nullptr && cta == 0;
+      unsigned long long tw[2] = {0, 0};
+      const long long tstart = tr ? clock64() : 0;
       for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
         const int row = a.x_row + tile * a.tile_tokens;
         for (int kc = 0; ok && kc < nkb; ++kc) {
+          const long long w0 = tr ? clock64() : 0;
           ok = ptx::mbar_wait(&xempty[px.stage], px.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kc);
           if (!ok) break;
+          if (tr) tw[0] += clock64() - w0;
           const uint32_t sx = smem_base + Cfg::kXOff + px.stage * 2 * kABytes;
           ptx::mbar_arrive_expect_tx(&xfull[px.stage], 2 * kABytes);
           ptx::tma_load_2d_hint(sx, &a.tm_x, &xfull[px.stage], kc * kBK, row, ptx::kEvictFirst);
           ptx::tma_load_2d_hint(sx + kABytes, &a.tm_x, &xfull[px.stage], kc * kBK, row + a.t_alloc, ptx::kEvictFirst);
           px.advance<Cfg::kXStages>();
           for (int p = 0; p < P; ++p) {
+            const long long w1 = tr ? clock64() : 0;
             ok = ptx::mbar_wait(&wempty[pw.stage], pw.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)(kc * 4 + p));
             if (!ok) break;
+            if (tr) tw[1] += clock64() - w1;
             const uint32_t sw = smem_base + Cfg::kWOff + pw.stage * Cfg::kSlabBytes;
             ptx::mbar_arrive_expect_tx(&wfull[pw.stage], Cfg::kSlabBytes);
             const int c0 = p * a.cin + kc * kBK;
@@ -175,6 +186,11 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
           }
         }
       }
+      if (tr) {
+        a.trace[52] = tw[0];
+        a.trace[53] = tw[1];
+        a.trace[54] = clock64() - tstart;
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -182,20 +198,28 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
       bool ok = true;
       int it = 0;
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(kTileRows, STACKED ? 2 * COUT : COUT);
+      const bool tr = a.trace != nullptr && cta == 0;
+      unsigned long long tw[4] = {0, 0, 0, 0};
+      const long long tstart = tr ? clock64() : 0;
       for (int tile = cta; ok && tile < a.n_tiles; tile += ncta, ++it) {
         const int acc = it % Cfg::kAccBufs;
         const int use = it / Cfg::kAccBufs;
+        const long long w0 = tr ? clock64() : 0;
         ok = ptx::mbar_wait(&tempty[acc], (use & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
         if (!ok) break;
+        if (tr) tw[0] += clock64() - w0;
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + acc * Cfg::kAccCols;
         bool first = true;
         for (int kc = 0; ok && kc < nkb; ++kc) {
           for (int p = 0; p < P; ++p) {
+            long long w1 = tr ? clock64() : 0;
             ok = ptx::mbar_wait(&afull[pa.stage], pa.phase, a.dbg, kDbgMmaAFull | (unsigned)(kc * 4 + p));
             if (!ok) break;
+            if (tr) { const long long n_ = clock64(); tw[1] += n_ - w1; w1 = n_; }
             ok = ptx::mbar_wait(&wfull[pw.stage], pw.phase, a.dbg, kDbgMmaFull | (unsigned)(kc * 4 + p));
             if (!ok) break;
+            if (tr) { const long long n_ = clock64(); tw[2] += n_ - w1; w1 = n_; }
             ptx::tc_fence_after();
             const uint32_t ta = tmem_base + Cfg::kAOffCols + pa.stage * Cfg::kSlotCols;
             const uint32_t sw = smem_base + Cfg::kWOff + pw.stage * Cfg::kSlabBytes;
@@ -216,20 +240,30 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
             ptx::umma_commit(&wempty[pw.stage]);
             pa.advance<Cfg::kASlots>();
             pw.advance<Cfg::kWStages>();
+            if (tr) tw[3] += clock64() - w1;
           }
         }
         if (ok) ptx::umma_commit(&tfull[acc]);
+      }
+      if (tr) {
+        for (int i = 0; i < 4; ++i) a.trace[40 + i] = tw[i];
+        a.trace[44] = clock64() - tstart;
       }
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
+    const bool tr = a.trace != nullptr && cta == 0 && q == 0 && lane == 0;
+    unsigned long long tw[2] = {0, 0};
+    const long long tstart = tr ? clock64() : 0;
     for (int tile = cta; ok && tile < a.n_tiles; tile += ncta, ++it) {
       const int acc = it % Cfg::kAccBufs;
       const int use = it / Cfg::kAccBufs;
+      long long w0 = tr ? clock64() : 0;
       ok = ptx::mbar_wait(&tfull[acc], use & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
+      if (tr) { const long long n_ = clock64(); tw[0] += n_ - w0; w0 = n_; }
       ptx::tc_fence_after();
       const int row = q * 32 + lane;
       const long long tok = (long long)tile * a.tile_tokens + row;
@@ -238,6 +272,12 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      if (tr) tw[1] += clock64() - w0;
+    }
+    if (tr) {
+      a.trace[48] = tw[0];
+      a.trace[49] = tw[1];
+      a.trace[50] = clock64() - tstart;
     }
   } else if (warp >= 8) {
     // ---- mix: thread = token row (TMEM lane), this warp's half of the K-block's 64 channels -------------
@@ -275,10 +315,17 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAOffCols + 16 * h;
     PipeState px, pa;
     bool ok = true;
+    const bool tr = a.trace != nullptr && cta == 0 && warp == 8 && lane == 0;
+    unsigned long long tw[4] = {0, 0, 0, 0};
+    unsigned long long nslots = 0;
+    long long tc = 0;
+    const long long tstart = tr ? clock64() : 0;
     for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
       for (int kc = 0; ok && kc < nkb; ++kc) {
+        if (tr) tc = clock64();
         ok = ptx::mbar_wait(&xfull[px.stage], px.phase, a.dbg, kDbgMixXFull | (unsigned)kc);
         if (!ok) break;
+        if (tr) { const long long n_ = clock64(); tw[0] += n_ - tc; tc = n_; }
         const uint8_t *xs = smem + Cfg::kXOff + px.stage * 2 * kABytes;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {  // unrolled so that the CSR register arrays are indexed statically
@@ -319,8 +366,10 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
               split8(acc8, oh + 4 * j, ol + 4 * j);
             }
           }
+          if (tr) { const long long n_ = clock64(); tw[1] += n_ - tc; tc = n_; }
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgMixAEmpty | (unsigned)(kc * 4 + p));
           if (!ok) break;
+          if (tr) { const long long n_ = clock64(); tw[2] += n_ - tc; tc = n_; }
           ptx::tc_fence_after();
           const uint32_t ta = lane_addr + pa.stage * Cfg::kSlotCols;
           ptx::tmem_st_32x16(ta, oh);
@@ -330,12 +379,18 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&afull[pa.stage]);
           pa.advance<Cfg::kASlots>();
+          if (tr) { const long long n_ = clock64(); tw[3] += n_ - tc; tc = n_; ++nslots; }
         }
         if (!ok) break;
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&xempty[px.stage]);  // this warp is done reading the input K-block
         px.advance<Cfg::kXStages>();
       }
+    }
+    if (tr) {
+      for (int i = 0; i < 4; ++i) a.trace[32 + i] = tw[i];
+      a.trace[36] = clock64() - tstart;
+      a.trace[37] = nslots;
     }
   }
   ptx::tc_fence_before();

@@ -29,3 +29,73 @@ def all_gather_logits(local, n_streams, group=None):
     bufs = [torch.empty((width,) + tail, dtype=local.dtype, device=local.device) for _ in range(world)]
     dist.all_gather(bufs, send, group=group)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
+class LogitGather:
+    """The same all-gather for a serving loop: buffers allocated once, the collective issued on a side stream so
+    that the next step's kernels do not wait for it ("overlap with the next step on a side
+    stream").  ``launch(local)`` returns immediately; ``result()`` makes the current stream wait for the newest
+    gather and returns the (n_streams, classes) matrix in global stream order.  Two result buffers alternate, so a
+    gather may still be in flight while the previous result is being read."""
+
+    def __init__(self, n_streams, classes, device, dtype=torch.float32, group=None):
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.n_streams, self.classes = int(n_streams), int(classes)
+        self.device = torch.device(device)
+        self._last = None
+        if not self.active:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.counts = [hi - lo for lo, hi in (shard_range(n_streams, r, world) for r in range(world))]
+        self.width = max(self.counts)
+        self.even = all(c == self.width for c in self.counts)
+        self.n_local = self.counts[rank]
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.send = torch.zeros((self.width, classes), dtype=dtype, device=self.device)
+        self.recv = [torch.empty((world * self.width, classes), dtype=dtype, device=self.device) for _ in range(2)]
+        self.out = [torch.empty((n_streams, classes), dtype=dtype, device=self.device) for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)] if self.stream is not None else [None, None]
+        self.turn = 0
+
+    def launch(self, local):
+        if not self.active:
+            self._last = local
+            return
+        b = self.turn
+        self.turn ^= 1
+        if self.stream is None:  # CPU / gloo: synchronous
+            self.send[: self.n_local].copy_(local)
+            dist.all_gather_into_tensor(self.recv[b], self.send, group=self.group)
+            self._compact(b)
+            self._last = b
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)  # the step's logits are complete
+            local.record_stream(self.stream)
+            self.send[: self.n_local].copy_(local, non_blocking=True)
+            dist.all_gather_into_tensor(self.recv[b], self.send, group=self.group)
+            self._compact(b)
+            self.done[b].record(self.stream)
+        self._last = b
+
+    def _compact(self, b):
+        if self.even:
+            return
+        lo = 0
+        for r, c in enumerate(self.counts):  # drop the padding rows of the short shards
+            self.out[b][lo:lo + c].copy_(self.recv[b][r * self.width:r * self.width + c], non_blocking=True)
+            lo += c
+
+    def result(self):
+        """Gathered logits of the newest ``launch`` (the current stream is made to wait for them)."""
+        if not self.active:
+            return self._last
+        b = self._last
+        if b is None:
+            return None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_event(self.done[b])
+        return self.recv[b] if self.even else self.out[b]

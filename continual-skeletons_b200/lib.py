@@ -90,6 +90,7 @@ SYMBOLS = {
     "cosk_profile_read": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "cosk_trace_read": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32]),
     "cosk_device_error": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
+    "cosk_describe": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_size_t]),
     "cosk_last_error": (ctypes.c_char_p, [_P]),
     "cosk_version": (ctypes.c_char_p, []),
 }

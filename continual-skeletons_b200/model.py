@@ -449,6 +449,15 @@ class _CoBase(nn.Module):
         e.check(e.lib.cosk_device_error(e.h, ctypes.byref(code)), "cosk_device_error")
         return int(code.value)
 
+    def knobs(self):
+        """The kernel selection of the engine (cosk_describe): runtime knobs and the kernel serving each block."""
+        import json
+
+        e = self._engine
+        buf = ctypes.create_string_buffer(8192)
+        e.check(e.lib.cosk_describe(e.h, buf, len(buf)), "cosk_describe")
+        return json.loads(buf.value.decode())
+
     def trace_read(self, n=24):
         e = self._engine
         buf = (ctypes.c_uint64 * n)()

@@ -146,7 +146,8 @@ int64_t cosk_launch_count(const cosk_model *m);
 int cosk_block_uses_tensor_cores(const cosk_model *m, int32_t block);
 
 /* Per-kernel-kind device timing with CUDA events on the launching stream.
- * kinds: 0 input, 1 gcn, 2 tcn, 3 pool+fc, 4 attention half of the adaptive gcn; enable before the timed region, then read. */
+ * kinds: 0 input, 1 gcn, 2 tcn, 3 pool+fc, 4 attention half of the adaptive gcn, 5 fused block step (graph conv + temporal
+ * conv of a 64 -> 64 block in one kernel); enable before the timed region, then read. */
 int cosk_profile_enable(cosk_model *m, int32_t on);
 /* Sums the event-measured device time (ms) and launch count of (kind, block) since enable;
  * block < 0 sums over blocks.  Synchronises the recorded events. */
@@ -161,6 +162,12 @@ int cosk_device_error(cosk_model *m, uint32_t *code);
  * buffer, write planes}, [5] drain total, [6] work items, [8..9] mix warp {wait planes, gather + store},
  * [16..18] MMA thread {wait accumulator free, wait operands, total}.  Debug aid. */
 int cosk_trace_read(cosk_model *m, uint64_t *out, int32_t n);
+
+/* The kernel selection this handle runs with, as a JSON object in `buf` (NUL-terminated, at most n bytes): the value of
+ * every runtime knob read from the COSK_* environment at cosk_create and, per block, which graph-conv / temporal-conv
+ * kernel serves it.  Valid after cosk_set_batch (weights prepared).  bench.py echoes it in its JSON line, so the
+ * configuration behind a measured number is on record. */
+int cosk_describe(const cosk_model *m, char *buf, size_t n);
 
 const char *cosk_last_error(const cosk_model *m);
 const char *cosk_version(void);

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from continual_skeletons_b200 import all_gather_logits, shard_range
+from continual_skeletons_b200 import LogitGather, all_gather_logits, shard_range
 
 
 def test_shard_range_partitions():
@@ -27,7 +27,13 @@ def _worker(rank, world, port, n_streams, ret):
     full = torch.arange(n_streams * 5, dtype=torch.float32).view(n_streams, 5)
     lo, hi = shard_range(n_streams, rank, world)
     got = all_gather_logits(full[lo:hi].clone(), n_streams)
-    ret[rank] = bool(torch.equal(got, full))
+    ok = bool(torch.equal(got, full))
+    # the pre-allocated serving-loop form of the same collective: two launches (buffers alternate), uneven shards compacted
+    g = LogitGather(n_streams, 5, "cpu")
+    for k in (1.0, 2.0):
+        g.launch(full[lo:hi] * k)
+        ok = ok and bool(torch.equal(g.result(), full * k))
+    ret[rank] = ok
     dist.destroy_process_group()
 
 
@@ -50,3 +56,10 @@ def test_all_gather_logits_gloo_world2():
 def test_all_gather_is_identity_without_process_group():
     x = torch.rand(3, 4)
     assert all_gather_logits(x, 3) is x
+
+
+def test_logit_gather_single_process_passthrough():
+    g = LogitGather(3, 4, "cpu")
+    x = torch.rand(3, 4)
+    g.launch(x)
+    assert g.result() is x
