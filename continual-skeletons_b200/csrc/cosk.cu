@@ -72,6 +72,7 @@ struct BlockW {
   } qchunk[2];
   int mix_max_nz = 0;
   int gcn_parts = 4;  // accumulator column groups of the tensor-core graph conv (3 or 4)
+  bool gcn_folded = false;  // gcn_residual folded into W_0 on the host (every self link exactly 1): no residual rows, three groups
   int mix_max_row12 = 0;  // most non-zeros of partitions 1 and 2 together for one output vertex
   bool mix_diag0 = true;  // partition 0 has only self links
   // device, tensor-core format: [2*cout rows (hi, lo)][K] bf16
@@ -83,9 +84,7 @@ struct BlockW {
   bool gcnp_ready = false;  // weights of the pre-mix form are uploaded (k_tc_gcnp and the fused block kernel use them)
   bool fuse = false;        // this block's step runs as ONE kernel (k_tc_block64)
   CUtensorMap map_tcn_w_full;  // temporal-conv weights with a 2*cout-row box: hi and lo rows in one stacked slab
-  __nv_bfloat16 *d_blk_gw16 = nullptr;  // graph-conv weights of the fused kernel: [2*cout rows][blk_parts*cin], K-blocks in mix-slot order
-  CUtensorMap map_blk_gw;
-  int blk_parts = 4;
+
   int gcnp_parts = 3;
   __nv_bfloat16 *d_gcnp_w16 = nullptr;
   CUtensorMap map_gcnp_w;
@@ -128,8 +127,8 @@ struct cosk_model {
   int gcn_premix = 0;  // which plain graph-conv widths run on the standalone pre-mix / A-in-TMEM kernel k_tc_gcnp (bit 0: 64, bit 1: 128,
                        // bit 2: 256 output channels); the rest stays on k_tc_gcn (COSK_GCN_PREMIX).  Off: measured slower standalone
                        // (profiles/r2a_gcnp_ab.txt) -- its CUDA-core mix only pays off hidden under the temporal conv's HBM stream
+  int gcn_fold_unit = 1;  // k_tc_gcn: fold the gcn_residual branch into W_0 when every self link is exactly 1 (COSK_GCN_FOLD_UNIT=0 disables)
   int fuse_block = 1;  // 64 -> 64 identity-residual blocks: graph conv + temporal conv in one kernel per step (COSK_FUSE_BLOCK=0: two kernels)
-  int gcnp_identity_mma = 3;  // widths whose identity gcn_residual rides in the pre-mix GEMM as a 4th part (same bits; others: epilogue add)
   int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
   EncodeTiledFn encode = nullptr;
@@ -408,7 +407,15 @@ int prepare(cosk_model *m) {
       // slack to add the input rows and the narrower accumulator saves MMA columns and TMEM reads (measured -8 %)
       const bool ident_mma = m->gcn_identity_mma == 1 || (m->gcn_identity_mma == 3 && bc.cin < 256);
       b.gcn_res_in_mix = m->gcn_identity_mma >= 2;
-      const int P = b.gcn_parts = adaptive ? ((res_conv || bc.cin == kBK) ? 4 : 3) : ((res_conv || ident_mma) ? 4 : 3);
+      // Every self link exactly 1 (A_0 = I with graph_attn's diagonal at 1, the reference initialisation): the own-row term of
+      // partition 0 and the gcn_residual branch act on the same rows, x W_0^T + x R^T = x (W_0 + R)^T, so the residual (identity
+      // or folded conv) is added into W_0 on the host and the accumulator shrinks to three column groups: a quarter fewer MMAs
+      // and TMEM reads, no residual rows fetched.  Trained self-link coefficients keep the four-group form.
+      bool unit_diag = !adaptive && b.mix_diag0 && m->gcn_fold_unit;
+      for (int w0 = 0; unit_diag && w0 < V; ++w0) unit_diag = (ptr[w0 + 1] - ptr[w0] == 1 && val[ptr[w0]] == 1.0f);
+      b.gcn_folded = unit_diag;
+      if (unit_diag) b.gcn_res_in_mix = false;
+      const int P = b.gcn_parts = adaptive ? ((res_conv || bc.cin == kBK) ? 4 : 3) : (unit_diag ? 3 : ((res_conv || ident_mma) ? 4 : 3));
       std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
       for (int o = 0; o < bc.cout; ++o)
         for (int part = 0; part < P; ++part) {
@@ -417,6 +424,12 @@ int prepare(cosk_model *m) {
             memcpy(&re[r * bc.cin], &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
           else
             re[r * bc.cin + o] = 1.0f;
+          if (unit_diag && part == 0) {
+            if (res_conv)
+              for (int k = 0; k < bc.cin; ++k) re[r * bc.cin + k] += b.gcn_w[(size_t)o * Kg + (size_t)3 * bc.cin + k];
+            else
+              re[r * bc.cin + o] += 1.0f;
+          }
         }
       std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
@@ -431,20 +444,29 @@ int prepare(cosk_model *m) {
       b.gcnp_ready = b.tc_gcn && !adaptive && !attention && tc_width(bc.cout) && part_max <= kPartSrcMax;
       b.tc_gcnp = b.gcnp_ready && (m->gcn_premix & wbit);
       if (b.gcnp_ready) {
-        const bool ident_mma = !res_conv && (m->gcnp_identity_mma & wbit);
-        const int P = b.gcnp_parts = (res_conv || ident_mma) ? 4 : 3;
+        b.gcnp_unit_diag = true;
+        for (int w0 = 0; w0 < V; ++w0) b.gcnp_unit_diag &= (ptr[w0 + 1] - ptr[w0] == 1 && val[ptr[w0]] == 1.0f);
+        // K-blocks in the order the mix warps fill their A slots: the plain input rows (gcn_residual weights: folded 1x1 conv
+        // or identity; plus W_0 when every self link is exactly 1, so that x and 1*x share one part), [W_0 on a0*x], W_1, W_2
+        const int P = b.gcnp_parts = b.gcnp_unit_diag ? 3 : 4;
         const int K = P * bc.cin;
         std::vector<float> w((size_t)bc.cout * K, 0.f);
         for (int o = 0; o < bc.cout; ++o) {
-          memcpy(&w[(size_t)o * K], &b.gcn_w[(size_t)o * Kg], sizeof(float) * std::min(K, Kg));
-          if (ident_mma) w[(size_t)o * K + 3 * bc.cin + o] = 1.0f;
+          float *row = &w[(size_t)o * K];
+          const float *src = &b.gcn_w[(size_t)o * Kg];
+          if (res_conv) memcpy(row, src + 3 * bc.cin, sizeof(float) * bc.cin);
+          else row[o] = 1.0f;
+          if (b.gcnp_unit_diag) {
+            for (int k = 0; k < bc.cin; ++k) row[k] += src[k];
+            memcpy(row + bc.cin, src + bc.cin, sizeof(float) * 2 * bc.cin);
+          } else {
+            memcpy(row + bc.cin, src, sizeof(float) * 3 * bc.cin);
+          }
         }
         std::vector<uint16_t> s = split_rows(w, bc.cout, K);
         if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcnp_w16), s.data(), s.size()))) return rc;
         if ((rc = make_map(m, &b.map_gcnp_w, b.d_gcnp_w16, (uint64_t)K, (uint64_t)2 * bc.cout, (uint32_t)std::min(2 * bc.cout, 256)))) return rc;
         b.gcnp_stacked = bc.cout <= 128 && (m->gcnp_stacked & wbit);
-        b.gcnp_unit_diag = true;
-        for (int w0 = 0; w0 < V; ++w0) b.gcnp_unit_diag &= (ptr[w0 + 1] - ptr[w0] == 1 && val[ptr[w0]] == 1.0f);
       }
     }
     if (attention) {
@@ -572,27 +594,6 @@ int prepare(cosk_model *m) {
     // one kernel per block step: 64 -> 64 blocks with the identity residual riding in both GEMMs
     b.fuse = m->fuse_block && b.gcnp_ready && bc.cin == 64 && bc.cout == 64 && bc.stride == 1 &&
              bc.res_kind == COSK_RES_IDENTITY && b.tc_tcn && b.tcn_res_kblock && bc.gconv == COSK_GCONV_PLAIN;
-    if (b.fuse) {
-      // K-blocks in the order the mix warps fill their slots: the plain input rows (identity gcn_residual; plus W_0 when every
-      // self link is exactly 1, so that x and 1*x share one part), [W_0 on a0*x], W_1, W_2
-      const int P = b.blk_parts = b.gcnp_unit_diag ? 3 : 4;
-      const int K = P * bc.cin;
-      std::vector<float> w((size_t)bc.cout * K, 0.f);
-      for (int o = 0; o < bc.cout; ++o) {
-        float *row = &w[(size_t)o * K];
-        const float *src = &b.gcn_w[(size_t)o * Kg];
-        row[o] = 1.0f;  // identity gcn_residual (cin == cout)
-        if (b.gcnp_unit_diag) {
-          for (int k = 0; k < bc.cin; ++k) row[k] += src[k];
-          memcpy(row + bc.cin, src + bc.cin, sizeof(float) * 2 * bc.cin);
-        } else {
-          memcpy(row + bc.cin, src, sizeof(float) * 3 * bc.cin);
-        }
-      }
-      std::vector<uint16_t> s16 = split_rows(w, bc.cout, K);
-      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_blk_gw16), s16.data(), s16.size()))) return rc;
-      if ((rc = make_map(m, &b.map_blk_gw, b.d_blk_gw16, (uint64_t)K, (uint64_t)2 * bc.cout, (uint32_t)(2 * bc.cout)))) return rc;
-    }
   }
   m->prepared = true;
   return COSK_OK;
@@ -751,8 +752,9 @@ TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int
   a.wait_cnt = nullptr;
   a.wait_need = 0;
   a.epi.bias = b.d_gcn_b;
-  a.epi.r_hi = b.gcn_parts == 4 ? nullptr : in.hi(in_slot);  // P = 3: identity gcn_residual added by the drain warps
-  a.epi.r_lo = b.gcn_parts == 4 ? nullptr : in.lo(in_slot);
+  const bool epi_res = b.gcn_parts == 3 && !b.gcn_folded;  // identity gcn_residual added from the input rows by the drain / mix warps
+  a.epi.r_hi = epi_res ? in.hi(in_slot) : nullptr;
+  a.epi.r_lo = epi_res ? in.lo(in_slot) : nullptr;
   a.epi.cs_r = in.cs;
   a.epi.y_hi = b.ring.hi(ring_slot);
   a.epi.y_lo = b.ring.lo(ring_slot);
@@ -782,12 +784,10 @@ TcGcnpArgs make_gcnp_args(cosk_model *m, int i, const ActBuf &in, int in_slot, i
   a.mix_ptr = b.d_mix_ptr;
   a.mix_src = b.d_mix_src;
   a.mix_val = b.d_mix_val;
-  a.unit_diag = b.gcnp_unit_diag ? 1 : 0;
   a.trace = m->d_trace;
   a.epi.bias = b.d_gcn_b;
-  const bool epi_res = b.gcnp_parts == 3;  // identity gcn_residual added by the epilogue from the input rows
-  a.epi.r_hi = epi_res ? in.hi(in_slot) : nullptr;
-  a.epi.r_lo = epi_res ? in.lo(in_slot) : nullptr;
+  a.epi.r_hi = nullptr;  // gcn_residual rides in the GEMM
+  a.epi.r_lo = nullptr;
   a.epi.cs_r = in.cs;
   a.epi.y_hi = b.ring.hi(ring_slot);
   a.epi.y_lo = b.ring.lo(ring_slot);
@@ -1257,9 +1257,9 @@ int run_block64(cosk_model *m, int i, const ActBuf &in, int in_slot, long long n
   TcBlockArgs a;
   a.tm_x = in.map;
   a.tm_ring = b.ring.map;
-  a.tm_gw = b.map_blk_gw;
+  a.tm_gw = b.map_gcnp_w;
   a.tm_tw = b.map_tcn_w_full;
-  a.n_parts = b.blk_parts;
+  a.n_parts = b.gcnp_parts;
   a.x_row = (int)in.row_hi(in_slot);
   a.res_row = fire ? (int)in.row_hi(res_slot) : 0;
   for (int k = 0; k < kTaps - 1; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
@@ -1444,7 +1444,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
   if (const char *e = getenv("COSK_GCN_PREMIX")) m->gcn_premix = atoi(e);
   if (const char *e = getenv("COSK_FUSE_BLOCK")) m->fuse_block = atoi(e);
-  if (const char *e = getenv("COSK_GCNP_IDENTITY_MMA")) m->gcnp_identity_mma = atoi(e);
+  if (const char *e = getenv("COSK_GCN_FOLD_UNIT")) m->gcn_fold_unit = atoi(e);
   if (const char *e = getenv("COSK_GCNP_STACKED")) m->gcnp_stacked = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
   if (const char *e = getenv("COSK_ATTN_TC")) m->attn_tc = atoi(e);
@@ -1515,7 +1515,6 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_adj);
     dfree(b.d_gcn_w16);
     dfree(b.d_gcnp_w16);
-    dfree(b.d_blk_gw16);
     dfree(b.d_tcn_w16);
     dfree(b.d_att_w16);
     dfree(b.d_sa_scale);
@@ -1759,10 +1758,10 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
   char t[1024];
   snprintf(t, sizeof t,
            "\"version\": \"%s\", \"path\": \"%s\", \"pdl\": %d, \"tcn_pair_mask\": %d, \"tcn_reverse\": %d, \"tcn_identity_mma\": %d, "
-           "\"fuse_block\": %d, \"gcn_premix\": %d, \"gcnp_identity_mma\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
+           "\"fuse_block\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
            "\"sa_fused\": %d, \"attn_tc\": %d, \"agcn_tc\": %d, \"trace\": %d, ",
            cosk_version(), m->cfg.path == COSK_PATH_AUTO ? "auto" : "simt", m->pdl, m->pair_mask, m->tcn_reverse, m->tcn_identity_mma,
-           m->fuse_block, m->gcn_premix, m->gcnp_identity_mma, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
+           m->fuse_block, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
            m->d_trace ? 1 : 0);
   o += t;
   o += "\"blocks\": [";

@@ -12,9 +12,14 @@
 // the epilogue drains a quarter of what k_tc_gcn drains and is the temporal conv's plain row epilogue; the mixed
 // operand never touches shared memory.
 //
-// Roles (512 threads): warp 0 TMA producer (input tile K-blocks + weight slabs), warp 1 MMA issuer + TMEM owner,
-// warps 4-7 epilogue (TMEM -> bias / residual / ReLU -> split -> 128-bit stores), warps 8-15 mix (two warps per
+// Roles (512 threads): warp 0 input-tile producer, warp 2 weight-slab producer (independent rings), warp 1 MMA issuer +
+// TMEM owner, warps 4-7 epilogue (TMEM -> bias / ReLU -> split -> 128-bit stores), warps 8-15 mix (two warps per
 // TMEM lane quarter, each half of the 64 channels of a K-block).
+// The mix works in two passes per K-block so that every input element is unpacked once instead of once per adjacency
+// entry: the raw hi / lo words of the own row go to registers and, unchanged, into the first A slot ("plain x": it carries
+// the gcn_residual weights -- identity or folded 1x1 conv -- plus W_0 when every self link is exactly 1); x = hi + lo is
+// then written back IN PLACE over the staged tile as fp32 rows, from which partitions 1 and 2 gather with one FMA per
+// adjacency entry and element (first version: 15 k warp-instructions per tile, this one ~6 k; profiles/r2a, r2c).
 // TMEM: [accumulator buffers][ring of 4 A slots x 64 columns: 32 columns hi + 32 columns lo of one (K-block, part)].
 #pragma once
 #include "tc_kernels.cuh"
@@ -31,19 +36,19 @@ enum : unsigned int {
 
 struct TcGcnpArgs {
   CUtensorMap tm_x;  // block input ring [kOutSlots*2*t_alloc rows][cin], box {64, 128}
-  CUtensorMap tm_w;  // [2*cout rows: hi rows, then lo rows][n_parts*cin], box {64, min(2*cout, 256)}; K = part*cin + c
+  CUtensorMap tm_w;  // [2*cout rows: hi rows, then lo rows][n_parts*cin], box {64, min(2*cout, 256)}; K = part*cin + c, parts in
+                     // A-slot order: plain x (gcn_residual weights [+ W_0 if every self link is 1]), [W_0 on a0*x], W_1, W_2
   int x_row;         // first row of the hi plane of the input slot
   int t_alloc;
   int cin;      // multiple of 64
-  int n_parts;  // 3: partitions only; 4: + the plain input rows (folded gcn_residual conv, or identity weights)
+  int n_parts;  // 3: self links are exactly 1 (W_0 folded into the plain-x part); 4: separate a0*x part
   int V;
   int n_tiles, tile_tokens;
   long long n_tokens;
   const int *mix_ptr;  // CSR over (partition * V + output vertex); partition 0 must be diagonal (self links)
   const int *mix_src;
   const float *mix_val;
-  int unit_diag;  // 1: every self-link coefficient is exactly 1, so part 0 is a copy of the input rows
-  EpiArgs epi;    // r_hi / r_lo = input rows when the identity gcn_residual is added by the epilogue (n_parts == 3)
+  EpiArgs epi;  // no residual rows: gcn_residual rides in the GEMM (plain-x part)
   unsigned long long *trace;  // optional phase timers of CTA 0 (COSK_TRACE=1), SM clock cycles: [32..37] mix warp {wait input
                               // K-block, compute, wait A slot, store + signal, total, slots}; [40..44] MMA thread {wait accumulator,
                               // wait A slot, wait weights, issue, total}; [48..50] epilogue warp {wait accumulator, work, total};
@@ -109,13 +114,16 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
   uint64_t *aempty = afull + Cfg::kASlots;
   uint64_t *tfull = aempty + Cfg::kASlots;
   uint64_t *tempty = tfull + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  uint64_t *mixbar = tempty + 2;  // two rendezvous points of the eight mix warps per K-block
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mixbar + 2);
   float *bias_s = reinterpret_cast<float *>(smem + Cfg::kBiasOff);
   const uint32_t smem_base = ptx::smem_u32(smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_trigger();
   if (threadIdx.x == 0) {
+    ptx::mbar_init(&mixbar[0], 8);
+    ptx::mbar_init(&mixbar[1], 8);
     for (int s = 0; s < Cfg::kXStages; ++s) {
       ptx::mbar_init(&xfull[s], 1);
       ptx::mbar_init(&xempty[s], 8);  // the eight mix warps
@@ -150,11 +158,12 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
   const int P = a.n_parts;
 
   if (warp == 0) {
+    // ---- input-tile producer: the K-blocks of every tile's input rows ------------------------------------
     if (lane == 0) {
-      PipeState px, pw;
+      PipeState px;
       bool ok = true;
       const bool tr = a.trace != nullptr && cta == 0;
-      unsigned long long tw[2] = {0, 0};
+      unsigned long long tw = 0;
       const long long tstart = tr ? clock64() : 0;
       for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
         const int row = a.x_row + tile * a.tile_tokens;
@@ -162,17 +171,33 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
           const long long w0 = tr ? clock64() : 0;
           ok = ptx::mbar_wait(&xempty[px.stage], px.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kc);
           if (!ok) break;
-          if (tr) tw[0] += clock64() - w0;
+          if (tr) tw += clock64() - w0;
           const uint32_t sx = smem_base + Cfg::kXOff + px.stage * 2 * kABytes;
           ptx::mbar_arrive_expect_tx(&xfull[px.stage], 2 * kABytes);
           ptx::tma_load_2d_hint(sx, &a.tm_x, &xfull[px.stage], kc * kBK, row, ptx::kEvictFirst);
           ptx::tma_load_2d_hint(sx + kABytes, &a.tm_x, &xfull[px.stage], kc * kBK, row + a.t_alloc, ptx::kEvictFirst);
           px.advance<Cfg::kXStages>();
+        }
+      }
+      if (tr) {
+        a.trace[52] = tw;
+        a.trace[54] = clock64() - tstart;
+      }
+    }
+  } else if (warp == 2) {
+    // ---- weight producer: one slab per (K-block, part), in the order the GEMM eats them --------------------
+    if (lane == 0) {
+      PipeState pw;
+      bool ok = true;
+      const bool tr = a.trace != nullptr && cta == 0;
+      unsigned long long tw = 0;
+      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+        for (int kc = 0; ok && kc < nkb; ++kc) {
           for (int p = 0; p < P; ++p) {
             const long long w1 = tr ? clock64() : 0;
             ok = ptx::mbar_wait(&wempty[pw.stage], pw.phase ^ 1, a.dbg, kDbgProdEmpty | 0x800000u | (unsigned)(kc * 4 + p));
             if (!ok) break;
-            if (tr) tw[1] += clock64() - w1;
+            if (tr) tw += clock64() - w1;
             const uint32_t sw = smem_base + Cfg::kWOff + pw.stage * Cfg::kSlabBytes;
             ptx::mbar_arrive_expect_tx(&wfull[pw.stage], Cfg::kSlabBytes);
             const int c0 = p * a.cin + kc * kBK;
@@ -186,11 +211,7 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
           }
         }
       }
-      if (tr) {
-        a.trace[52] = tw[0];
-        a.trace[53] = tw[1];
-        a.trace[54] = clock64() - tstart;
-      }
+      if (tr) a.trace[53] = tw;
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -283,9 +304,10 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
     // ---- mix: thread = token row (TMEM lane), this warp's half of the K-block's 64 channels -------------
     const int q = warp & 3, h = (warp - 8) >> 2;
     const int row = q * 32 + lane;
-    // CSR of this row: tiles are skeleton aligned, so the source rows are tile invariant.  Unused entries
-    // carry a zero coefficient and point at the own row; loops run to the warp's maximum count.
-    int s_row[2][kPartSrcMax];
+    // CSR of this row (tile invariant: tiles are skeleton aligned).  Sources as byte offset of the fp32 row (its
+    // swizzle key is bits 8..10); unused entries carry a zero coefficient and point at the own row; loops run to
+    // the warp's maximum count.
+    uint32_t s_off[2][kPartSrcMax];
     float s_cf[2][kPartSrcMax];
     int nmax[2] = {0, 0};
     float d0 = 0.f;
@@ -303,7 +325,7 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
 #pragma unroll
         for (int e = 0; e < kPartSrcMax; ++e) {
           const bool on = e < n;
-          s_row[p][e] = on ? sk0 + a.mix_src[eb + e] : row;
+          s_off[p][e] = (uint32_t)(on ? sk0 + a.mix_src[eb + e] : row) * 256u;
           s_cf[p][e] = on ? a.mix_val[eb + e] : 0.f;
         }
         int m = n;
@@ -315,75 +337,132 @@ __device__ __forceinline__ void gcnp_body(const TcGcnpArgs &a, uint8_t *smem_raw
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + Cfg::kAOffCols + 16 * h;
     PipeState px, pa;
     bool ok = true;
+    uint32_t nk = 0;  // K-blocks mixed so far: parity of the two rendezvous barriers
     const bool tr = a.trace != nullptr && cta == 0 && warp == 8 && lane == 0;
     unsigned long long tw[4] = {0, 0, 0, 0};
     unsigned long long nslots = 0;
     long long tc = 0;
     const long long tstart = tr ? clock64() : 0;
+    auto lap = [&](int i) {
+      if (tr) {
+        const long long n_ = clock64();
+        tw[i] += n_ - tc;
+        tc = n_;
+      }
+    };
+    // one finished part -> its A slot in tensor memory
+    auto put = [&](const uint32_t (&oh)[16], const uint32_t (&ol)[16], unsigned code) {
+      lap(1);
+      ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgMixAEmpty | code);
+      if (!ok) return;
+      lap(2);
+      ptx::tc_fence_after();
+      const uint32_t ta = lane_addr + pa.stage * Cfg::kSlotCols;
+      ptx::tmem_st_32x16(ta, oh);
+      ptx::tmem_st_32x16(ta + 32, ol);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&afull[pa.stage]);
+      pa.advance<Cfg::kASlots>();
+      lap(3);
+      ++nslots;
+    };
+    // rendezvous of the mix warps through an mbarrier (bounded wait: a failed pipeline cannot park a warp forever)
+    auto mix_sync = [&](int which) {
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&mixbar[which]);
+      ok = ptx::mbar_wait(&mixbar[which], nk & 1u, a.dbg, kDbgMixXFull | 0x800000u | (unsigned)which);
+    };
     for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
-      for (int kc = 0; ok && kc < nkb; ++kc) {
+      for (int kc = 0; ok && kc < nkb; ++kc, ++nk) {
         if (tr) tc = clock64();
         ok = ptx::mbar_wait(&xfull[px.stage], px.phase, a.dbg, kDbgMixXFull | (unsigned)kc);
         if (!ok) break;
-        if (tr) { const long long n_ = clock64(); tw[0] += n_ - tc; tc = n_; }
-        const uint8_t *xs = smem + Cfg::kXOff + px.stage * 2 * kABytes;
+        lap(0);
+        uint8_t *xs = smem + Cfg::kXOff + px.stage * 2 * kABytes;
+        // pass 1: own row, raw words: 4 chunks of 8 channels per plane
+        uint32_t rh[16], rl[16];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {  // unrolled so that the CSR register arrays are indexed statically
-          if (p >= P) break;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = sw128_off(row, 4 * h + j);
+          const uint4 hv = *reinterpret_cast<const uint4 *>(xs + off);
+          const uint4 lv = *reinterpret_cast<const uint4 *>(xs + kABytes + off);
+          rh[4 * j] = hv.x; rh[4 * j + 1] = hv.y; rh[4 * j + 2] = hv.z; rh[4 * j + 3] = hv.w;
+          rl[4 * j] = lv.x; rl[4 * j + 1] = lv.y; rl[4 * j + 2] = lv.z; rl[4 * j + 3] = lv.w;
+        }
+        mix_sync(0);  // every raw word of the staged K-block is in registers: it may be overwritten
+        if (!ok) break;
+        // pass 2: x = hi + lo as fp32, in place: row r at bytes [256 r, 256 r + 256), 16-byte chunks XOR-swizzled with r & 7
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const float4 f4 = make_float4(bf16_lo_as_float(rh[2 * b]) + bf16_lo_as_float(rl[2 * b]), bf16_hi_as_float(rh[2 * b]) + bf16_hi_as_float(rl[2 * b]),
+                                        bf16_lo_as_float(rh[2 * b + 1]) + bf16_lo_as_float(rl[2 * b + 1]),
+                                        bf16_hi_as_float(rh[2 * b + 1]) + bf16_hi_as_float(rl[2 * b + 1]));
+          *reinterpret_cast<float4 *>(xs + row * 256 + (((8 * h + b) ^ (row & 7)) << 4)) = f4;
+        }
+        put(rh, rl, 0);  // part "plain x": the words pass through unchanged
+        if (!ok) break;
+        if (P == 4) {  // self links with a coefficient other than 1: a0 * x from the own registers
           uint32_t oh[16], ol[16];
-          if (p == 3 || (p == 0 && a.unit_diag)) {
-            // the plain input rows: hi / lo words pass through unchanged
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t off = sw128_off(row, 4 * h + j);
-              const uint4 hv = *reinterpret_cast<const uint4 *>(xs + off);
-              const uint4 lv = *reinterpret_cast<const uint4 *>(xs + kABytes + off);
-              oh[4 * j] = hv.x; oh[4 * j + 1] = hv.y; oh[4 * j + 2] = hv.z; oh[4 * j + 3] = hv.w;
-              ol[4 * j] = lv.x; ol[4 * j + 1] = lv.y; ol[4 * j + 2] = lv.z; ol[4 * j + 3] = lv.w;
+          for (int j = 0; j < 4; ++j) {
+            float a8[8];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              a8[2 * w] = d0 * (bf16_lo_as_float(rh[4 * j + w]) + bf16_lo_as_float(rl[4 * j + w]));
+              a8[2 * w + 1] = d0 * (bf16_hi_as_float(rh[4 * j + w]) + bf16_hi_as_float(rl[4 * j + w]));
             }
-          } else if (p == 0) {
+            split8(a8, oh + 4 * j, ol + 4 * j);
+          }
+          put(oh, ol, 1);
+          if (!ok) break;
+        }
+        mix_sync(1);  // fp32 rows complete
+        if (!ok) break;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t off = sw128_off(row, 4 * h + j);
-              float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              fma_chunk(acc8, d0, *reinterpret_cast<const uint4 *>(xs + off), *reinterpret_cast<const uint4 *>(xs + kABytes + off));
-              split8(acc8, oh + 4 * j, ol + 4 * j);
-            }
-          } else {
-            const int pp = p - 1;
-            const int n = nmax[pp];
+        for (int pp = 0; pp < 2; ++pp) {
+          const int n = nmax[pp];
+          uint32_t oh[16], ol[16];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int jj = 0; jj < 2; ++jj) {  // 16 channels at a time: four 16-byte loads in flight per adjacency entry
+            float acc[16];
 #pragma unroll
-              for (int e = 0; e < kPartSrcMax; ++e) {
-                if (e < n) {
-                  const uint32_t off = sw128_off(s_row[pp][e], 4 * h + j);
-                  fma_chunk(acc8, s_cf[pp][e], *reinterpret_cast<const uint4 *>(xs + off),
-                            *reinterpret_cast<const uint4 *>(xs + kABytes + off));
+            for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int e = 0; e < kPartSrcMax; ++e) {
+              if (e < n) {
+                const uint32_t off = s_off[pp][e];
+                const uint8_t *base = xs + off;
+                const uint32_t key = (off >> 8) & 7u;
+                float4 v[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) v[b] = *reinterpret_cast<const float4 *>(base + (((uint32_t)(8 * h + 4 * jj + b) ^ key) << 4));
+                const float cf = s_cf[pp][e];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                  acc[4 * b] = fmaf(cf, v[b].x, acc[4 * b]);
+                  acc[4 * b + 1] = fmaf(cf, v[b].y, acc[4 * b + 1]);
+                  acc[4 * b + 2] = fmaf(cf, v[b].z, acc[4 * b + 2]);
+                  acc[4 * b + 3] = fmaf(cf, v[b].w, acc[4 * b + 3]);
                 }
               }
-              split8(acc8, oh + 4 * j, ol + 4 * j);
             }
+            float lo8[8], hi8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              lo8[e] = acc[e];
+              hi8[e] = acc[8 + e];
+            }
+            split8(lo8, oh + 8 * jj, ol + 8 * jj);
+            split8(hi8, oh + 8 * jj + 4, ol + 8 * jj + 4);
           }
-          if (tr) { const long long n_ = clock64(); tw[1] += n_ - tc; tc = n_; }
-          ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgMixAEmpty | (unsigned)(kc * 4 + p));
+          put(oh, ol, 2 + pp);
           if (!ok) break;
-          if (tr) { const long long n_ = clock64(); tw[2] += n_ - tc; tc = n_; }
-          ptx::tc_fence_after();
-          const uint32_t ta = lane_addr + pa.stage * Cfg::kSlotCols;
-          ptx::tmem_st_32x16(ta, oh);
-          ptx::tmem_st_32x16(ta + 32, ol);
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&afull[pa.stage]);
-          pa.advance<Cfg::kASlots>();
-          if (tr) { const long long n_ = clock64(); tw[3] += n_ - tc; tc = n_; ++nslots; }
         }
         if (!ok) break;
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&xempty[px.stage]);  // this warp is done reading the input K-block
+        if (lane == 0) ptx::mbar_arrive(&xempty[px.stage]);  // this warp is done with the staged K-block
         px.advance<Cfg::kXStages>();
       }
     }
