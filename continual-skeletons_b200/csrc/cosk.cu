@@ -1302,13 +1302,19 @@ inline bool tcn_fires(long long n, int padding, int stride) {
 // co.AvgPool1d(P, stride 1, padding pp): the m-th pooled vector yields logits iff m >= P - 1 - pp.
 inline bool head_fires(long long m_, int pool_size, int pool_padding) { return m_ >= (long long)pool_size - 1 - pool_padding; }
 
-int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s) {
+// One step of the stack.  `enter` = 0: a new input frame x enters at the first block (cosk_step).  End-of-sequence flush
+// (forward_steps(pad_end=True) of the library: every temporal module is fed its own end padding once the clip is over,
+// module by module): `enter` = i in [0, n_blocks) pushes one ZERO frame into the temporal conv of block i (not through its
+// graph conv: co.forward_stepping modules have no padding), `enter` = n_blocks pushes one zero vector into the pooling
+// window; whatever that emits propagates through the later stages exactly like a regular step.
+int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s, int enter = 0,
+              bool flush = false) {
   const cosk_config &c = m->cfg;
   int rc;
   // input frame -> token rows (data_bn folded in)
   const int xslot = (int)(m->frame % kOutSlots);
   if ((rc = prof_mark(m, 0, -1, s))) return rc;
-  {
+  if (!flush) {
     const long long total = m->n_tokens * m->xin.cs;
     const int threads = 256;
     const long long blocks = (total + threads - 1) / threads;
@@ -1320,16 +1326,25 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   const ActBuf *in = &m->xin;
   bool alive = true;
   bool gcn_done = false;  // the graph conv of the current block already ran inside the previous block's merged launch
+  const bool head_flush = flush && enter >= c.n_blocks;
   for (int i = 0; i < c.n_blocks; ++i) {
     m->last_flags[i] = 0;
+    if (flush && (i < enter || head_flush)) {  // stages before the flushed one are over
+      in = &m->blk[i].out;
+      continue;
+    }
     if (!alive) continue;
     BlockW &b = m->blk[i];
     const cosk_block_cfg &bc = c.blocks[i];
     const long long n = b.n_in;  // index of this input == index of the predecessor's emission
     const int in_slot = (int)(n % kOutSlots);
     const bool fire = tcn_fires(n, c.padding, bc.stride);
-    const bool fused = b.fuse && !gcn_done && in->has_map;
-    if (fused) {
+    const bool zero_in = flush && i == enter;  // a zero frame enters the temporal conv directly
+    const bool fused = b.fuse && !gcn_done && in->has_map && !zero_in;
+    if (zero_in) {
+      const int rs = (int)(n % kRingSlots);
+      CK(cudaMemsetAsync(b.ring.hi(rs), 0, (size_t)2 * b.ring.t_alloc * b.ring.cs * sizeof(__nv_bfloat16), s));
+    } else if (fused) {
       const int res_slot = fire ? (int)((n - kResDelay) % kOutSlots) : 0;
       if ((rc = run_block64(m, i, *in, in_slot, n, fire, res_slot, (int)(b.n_out % kOutSlots), s))) return rc;
       if (fire) b.n_out++;
@@ -1354,15 +1369,16 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     in = &b.out;
   }
   int emit = 0;
+  if (head_flush && c.classes == 0) alive = false;  // nothing to flush without a pooling window
   if (alive) {
     const BlockW &last = m->blk[c.n_blocks - 1];
-    const int slot = (int)((last.n_out - 1) % kOutSlots);
+    const int slot = (int)(((last.n_out > 0 ? last.n_out : 1) - 1) % kOutSlots);
     if (c.classes > 0) {
       emit = head_fires(m->pool_n, c.pool_size, c.pool_padding) ? 1 : 0;
       if ((rc = prof_mark(m, 3, -1, s))) return rc;
       HeadArgs h;
-      h.y_hi = last.out.hi(slot);
-      h.y_lo = last.out.lo(slot);
+      h.y_hi = head_flush ? nullptr : last.out.hi(slot);  // nullptr: a zero vector enters the window
+      h.y_lo = head_flush ? nullptr : last.out.lo(slot);
       h.cs = last.out.cs;
       h.c = last.out.c;
       h.V = c.vertices;
@@ -1391,7 +1407,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   }
   if ((rc = prof_mark(m, -1, -1, s))) return rc;  // closes the last interval of this step
   m->last_flags[c.n_blocks] = emit;
-  m->frame++;
+  if (!flush) m->frame++;
   if (emitted) *emitted = emit;
   return COSK_OK;
 }
@@ -1672,9 +1688,10 @@ static int step_entry(cosk_model *m) {
   return COSK_OK;
 }
 
-static int step_guarded(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s) {
+static int step_guarded(cosk_model *m, const float *x, long long nc_stride, float *out, int32_t *emitted, cudaStream_t s, int enter = 0,
+                        bool flush = false) {
   int32_t em = 0;
-  int rc = step_impl(m, x, nc_stride, out, &em, s);
+  int rc = step_impl(m, x, nc_stride, out, &em, s, enter, flush);
   if (rc) {
     m->failed = true;  // counters may be partly advanced
     return rc;
@@ -1701,6 +1718,11 @@ int cosk_step(cosk_model *m, const float *x_dev, int64_t nc_stride, float *out_d
 
 int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride, int32_t max_out,
                int32_t *n_emitted, void *stream) {
+  return cosk_steps_ex(m, x_dev, T, out_dev, out_stride, max_out, n_emitted, stream, 0);
+}
+
+int cosk_steps_ex(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride, int32_t max_out,
+                  int32_t *n_emitted, void *stream, int32_t pad_end) {
   if (!m || !x_dev || !out_dev || T < 0) return COSK_ERR_ARG;
   int rc = step_entry(m);
   if (rc) return rc;
@@ -1715,6 +1737,26 @@ int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int
                       (cudaStream_t)stream);
     if (rc) return rc;
     cnt += em;
+  }
+  if (pad_end) {
+    // The clip is over: every temporal module flushes its end padding, module by module (first the blocks in order,
+    // `padding` zero frames into each temporal conv, then `pool_padding` zero vectors into the pooling window).  What a
+    // flush emits runs through the later stages at once (depth first), which yields the same output sequence as the
+    // library's module-by-module order because every stage is a causal sequential machine.
+    const int stages = m->cfg.n_blocks + 1;
+    for (int st = 0; st < stages; ++st) {
+      const int reps = st < m->cfg.n_blocks ? m->cfg.padding : (m->cfg.classes > 0 ? m->cfg.pool_padding : 0);
+      for (int z = 0; z < reps; ++z) {
+        int32_t em = 0;
+        const int32_t dst = cnt < max_out ? cnt : max_out - 1;
+        rc = step_guarded(m, nullptr, 0, out_dev + (long long)dst * out_stride, &em, (cudaStream_t)stream, st, true);
+        if (rc) return rc;
+        cnt += em;
+      }
+    }
+    // the padded frames are not part of the stream: the sequence ends here and the state starts over
+    rc = zero_state(m, (cudaStream_t)stream);
+    if (rc) return rc;
   }
   if (n_emitted) *n_emitted = cnt;
   return COSK_OK;

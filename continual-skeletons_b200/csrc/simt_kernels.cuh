@@ -768,7 +768,10 @@ __global__ void __launch_bounds__(256 * kHeadStreams) k_head(HeadArgs a) {
   const long long n = n0 + g;
   const bool live = n < a.n_streams;
   const int half = tid >> 7, t128 = tid & 127;
-  if (live) {
+  if (live && a.y_hi == nullptr) {
+    // end-of-sequence flush of the pooling window (pad_end): a zero vector enters (co.AvgPool1d's end padding)
+    for (int c = t128 + 128 * half; c < 2 * a.cs; c += 256) part[c] = 0.f;
+  } else if (live) {
     const long long tok0 = n * a.S * a.V;
     // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
     for (int cp = t128; cp < a.cs / 2; cp += 128) {

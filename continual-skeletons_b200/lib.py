@@ -79,6 +79,8 @@ SYMBOLS = {
     "cosk_reset": (ctypes.c_int, [_P]),
     "cosk_step": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.POINTER(ctypes.c_int32), _P]),
     "cosk_steps": (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _P]),
+    "cosk_steps_ex": (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _P,
+                                     ctypes.c_int32]),
     "cosk_state_bytes": (ctypes.c_int64, [_P]),
     "cosk_last_schedule": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]),
     "cosk_simulate_schedule": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),

@@ -493,17 +493,21 @@ class _CoBase(nn.Module):
             raise
         return out if em.value else None
 
-    def _steps(self, x, n_streams, T, shape_key):
+    def _steps(self, x, n_streams, T, shape_key, pad_end=False):
         e = self._sync(x.device)
         self._ensure_batch(e, shape_key, n_streams)
-        # upper bound on emissions: the last stage can emit at most once per `stride` frames
+        # upper bound on emissions: the last stage can emit at most once per `stride` frames; the end-of-sequence flush
+        # adds at most one emission per padded frame of any stage
         max_out = T // self.stride + 1
+        if pad_end:
+            max_out += self._pad * len(self._specs) + (self.pool_padding if self._head else 0) + 1
         oshape = self._out_shape(n_streams)
         out = torch.empty((max_out,) + oshape, dtype=torch.float32, device=x.device)
         n = ctypes.c_int32(0)
         try:
-            e.check(e.lib.cosk_steps(e.h, ctypes.c_void_p(x.data_ptr()), T, ctypes.c_void_p(out.data_ptr()),
-                                     int(np.prod(oshape)), max_out, ctypes.byref(n), self._stream(x)), "cosk_steps")
+            e.check(e.lib.cosk_steps_ex(e.h, ctypes.c_void_p(x.data_ptr()), T, ctypes.c_void_p(out.data_ptr()),
+                                        int(np.prod(oshape)), max_out, ctypes.byref(n), self._stream(x), 1 if pad_end else 0),
+                    "cosk_steps")
         except CoskError:
             self._shape = None
             raise
@@ -641,14 +645,14 @@ class CoModelBase(_CoBase):
 
     def forward_steps(self, input, pad_end=False, update_state=True):
         """input (N, C, T, V, S) -> (N, classes) for one emission, (N, classes, n) for several, None
-        for none (models/base.py:187-190,101)."""
-        if pad_end:
-            raise NotImplementedError("pad_end=True is a test helper of the library, not part of the model path")
+        for none (models/base.py:187-190,101).  ``pad_end=True`` (the library's end-of-clip flush, used by the reference's
+        tests): every temporal stage is fed its end padding after the clip, so the emissions equal the regular zero-padded
+        network's outputs over the whole clip; the state is reset afterwards (the padded frames are not part of the stream)."""
         if not update_state:
             raise NotImplementedError("update_state=False is not supported")
         x = self._check_input(input, 5)
         N, C, T, V, S = x.shape
-        out = self._steps(x, N, T, (N, C, V, S))
+        out = self._steps(x, N, T, (N, C, V, S), pad_end)
         if out is None:
             return None
         return out[0] if out.shape[0] == 1 else out.permute(1, 2, 0).contiguous()
@@ -740,9 +744,10 @@ class CoStack(_CoBase):
         x = self._check_input(input, 3)
         return self._step(x, x.shape[0], self._V)
 
-    def forward_steps(self, input):
-        """(B, C, T, V) -> (B, Cout, n, V) | None."""
+    def forward_steps(self, input, pad_end=False):
+        """(B, C, T, V) -> (B, Cout, n, V) | None.  ``pad_end``: flush every block's temporal end padding after the clip
+        (tests/test_cost_gcn.py:67,223,270,325 in the reference), state reset afterwards."""
         x = self._check_input(input, 4)
         B, C, T, V = x.shape
-        out = self._steps(x, B, T, (B, C, V))
+        out = self._steps(x, B, T, (B, C, V), pad_end)
         return None if out is None else out.permute(1, 2, 0, 3).contiguous()

@@ -128,6 +128,14 @@ int cosk_step(cosk_model *m, const float *x_dev, int64_t nc_stride, float *out_d
 int cosk_steps(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride,
                int32_t max_out, int32_t *n_emitted, void *stream);
 
+/* forward_steps(pad_end=True) of the un-vendored continual-inference library, which the reference's own block tests use
+ * (tests/test_cost_gcn.py:67,223,270,325): after the T frames every temporal module is fed its end padding -- `padding`
+ * zero frames into each block's temporal conv, `pool_padding` zero vectors into the pooling window -- so that the emissions
+ * equal the outputs of the regular zero-padded network on the whole clip.  The padded frames are not part of the stream:
+ * the state is reset (as by cosk_reset, asynchronously on `stream`) when the call returns.  pad_end = 0: cosk_steps. */
+int cosk_steps_ex(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, int64_t out_stride,
+                  int32_t max_out, int32_t *n_emitted, void *stream, int32_t pad_end);
+
 /* Introspection (parity of the integer schedule, roofline accounting). */
 int64_t cosk_state_bytes(const cosk_model *m);
 /* flags[i] = 1 iff block i emitted during the last cosk_step; flags[n_blocks] = head emitted. */

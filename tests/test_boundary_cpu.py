@@ -160,9 +160,17 @@ def test_host_bn_folding_matches_oracle(cin, cout, stride, residual, pad):
 def test_unsupported_arguments():
     m = cs.CoStGcn()
     with pytest.raises(NotImplementedError):
-        m.forward_steps(torch.rand(1, 3, 4, 25, 2), pad_end=True)
+        m.forward_steps(torch.rand(1, 3, 4, 25, 2), update_state=False)
     with pytest.raises(NotImplementedError):
         m.forward_step(torch.rand(1, 3, 25, 2), update_state=False)
+    # CoA-GCN implements the per-step path only: its clip forward is a different function in the reference
+    # (attention over all T frames, models/a_gcn/a_gcn.py:53-62) and is refused rather than approximated
+    a = cs.CoAGcn()
+    with pytest.raises(NotImplementedError):
+        a(torch.rand(1, 3, 4, 25, 2))
+    # no CPU path: host tensors are refused, pad_end or not
+    with pytest.raises(cs.CoskError):
+        m.forward_steps(torch.rand(1, 3, 4, 25, 2), pad_end=True)
 
 
 @pytest.mark.parametrize("cls,arch_fn", [(cs.CoStGcn, weights.cost_gcn_arch), (cs.CoStGcnMod, weights.cost_gcn_mod_arch)])
@@ -278,3 +286,22 @@ def test_cos_tr_host_model(golden):
     o = torch.einsum("bhtij,bhdtj->bhdti", w, v).reshape(B, 128, T, V)
     got = torch.relu(torch.einsum("oc,bctv->botv", t["gcn.w"], o) + t["gcn.b"].view(1, -1, 1, 1) + t["sa.skip_scale"].view(1, -1, 1, 1) * x)
     assert torch.allclose(got, want, atol=2e-5 * max(1.0, float(want.abs().max())))
+
+
+def test_bench_algorithmic_cost_matches_survey_totals():
+    """bench.py derives the roofline numerators from the block table; they must reproduce the totals SURVEY.md section
+    8(d) states (CoST-GCN 1.408 MB / 57.5 M MACs, CoST-GCN* 3.072 MB / 159.0 M MACs per stream-frame, Kinetics 1.014 MB /
+    41.0 M MACs) and the per-block figure of 70.4 kB per skeleton for a 64-channel block step."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = bench.algorithmic_cost("cost_gcn", v=25)
+    assert abs(a["state"] - 1.408e6) < 1 and abs(a["flops"] / 2 - 57.5e6) < 0.05e6
+    b = bench.algorithmic_cost("cost_gcn_mod", v=25)
+    assert abs(b["state"] - 3.072e6) < 1 and abs(b["flops"] / 2 - 159.0e6) < 0.05e6
+    k = bench.algorithmic_cost("cost_gcn", v=18)
+    assert abs(k["state"] - 1.01376e6) < 1 and abs(k["flops"] / 2 - 41.0e6) < 0.05e6
+    blk = a["blocks"][1]  # a 64 -> 64 block: 11 frames of 25 x 64 x 4 B per skeleton, two skeletons per stream
+    assert blk["gcn_bytes"] + blk["tcn_bytes"] == 2 * 70400

@@ -577,3 +577,79 @@ def test_widened_models_ragged_tiles(which, n_streams):
         if n_out:
             e = _rel_err(m.read_block(i).cpu(), feats[i][:, :, n_out - 1])
             assert e < 2e-4, (which, n_streams, i, e)
+
+
+# ---------------------------------------------------------------------------------------------
+# forward_steps(pad_end=True): the relations of the reference's own tests that flush the end padding
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["simt", "auto"])
+@pytest.mark.parametrize("rnd", [False, True])
+@pytest.mark.parametrize("idx", range(len(BLOCK_CASES)))
+def test_block_forward_steps_pad_end_equals_whole_clip(golden, idx, rnd, path):
+    """``co.forward_steps(sample, pad_end=True) == reg(sample)`` for every block kind
+    (tests/test_cost_gcn.py:67-68,223-224,270,325 in the reference): with the end padding flushed the emissions are the
+    regular zero-padded block's outputs over the WHOLE clip, not just the prefix stepping alone can produce."""
+    key, arch, sd, x, spec, stack = _block_setup(idx, rnd, path)
+    target = torch.from_numpy(golden["blocks"][key])
+    xd = x.to(DEV)
+    prefix = stack.forward_steps(xd).cpu()  # pad_end=False: target[:, :, :-delay] (tests/test_cost_gcn.py:219-220)
+    assert stack.device_error() == 0
+    n_prefix = prefix.shape[2]
+    assert n_prefix == target.shape[2] - arch.padding // spec.stride or arch.padding == 0
+    stack.clean_state()
+    full = stack.forward_steps(xd, pad_end=True).cpu()
+    assert stack.device_error() == 0
+    assert tuple(full.shape) == tuple(target.shape), (key, tuple(full.shape), tuple(target.shape))
+    assert _rel_err(full, target) < BLOCK_RTOL, (key, _rel_err(full, target))
+    assert torch.equal(full[:, :, :n_prefix], prefix)
+    # the padded frames are not part of the stream: the state starts over afterwards
+    again = stack.forward_steps(xd).cpu()
+    assert torch.equal(again, prefix)
+
+
+@pytest.mark.parametrize("path", ["simt", "auto"])
+def test_strided_three_block_stack_pad_end(path):
+    """tests/test_cost_gcn.py:273-326 in the reference: co.Sequential of three blocks (no residual, identity residual,
+    strided conv residual), ``forward_steps(pad_end=True)`` equals the regular stack on the clip -- here also with 64 / 128
+    channels so that the fused and tensor-core kernels take the flush path."""
+    for cin, cout in ((2, 4), (64, 128)):
+        blocks = [weights.BlockSpec(cin, cin, 1, False), weights.BlockSpec(cin, cin, 1, True), weights.BlockSpec(cin, cout, 2, True)]
+        arch = ArchSpec(blocks, padding=4, head=False, block_names=["0.", "1.", "2."])
+        sd = weights.make_state_dict(arch, seed=71, randomize=True)
+        x = weights.make_input((3, cin, 21, 25), seed=72)
+        with torch.no_grad():
+            target = regular.stack_features(x, sd, arch)
+        stack = cs.CoStack([cs.BlockSpec(b.cin, b.cout, b.stride, b.residual) for b in blocks], padding=4, kernel_path=path)
+        mapped = {}
+        for k, v in sd.items():
+            i, rest = k.split(".", 1)
+            kind = blocks[int(i)].res_kind
+            mapped[f"{i}.{rest}" if kind == 0 else (f"{i}.0.0.{rest}" if rest.startswith("residual") else f"{i}.0.1.{rest}")] = v
+        stack.load_state_dict(mapped, strict=True)
+        out = stack.forward_steps(x.to(DEV), pad_end=True)
+        assert stack.device_error() == 0
+        assert tuple(out.shape) == tuple(target.shape), (tuple(out.shape), tuple(target.shape))
+        assert _rel_err(out.cpu(), target) < 2e-4, _rel_err(out.cpu(), target)
+
+
+@pytest.mark.parametrize("cls,arch_fn,tag", [
+    (cs.CoStGcn, weights.cost_gcn_arch, "cost_gcn"),
+    (cs.CoStGcnMod, weights.cost_gcn_mod_arch, "cost_gcn_mod"),
+])
+def test_model_forward_steps_pad_end_equals_clip_network(cls, arch_fn, tag):
+    """Whole model: with the end padding of every block and of the pooling window flushed, forward_steps returns the
+    regular network's full output sequence (co.Sequential.forward of models/base.py:166-181 before the [:, :, 0] cut)."""
+    arch, sd, m = _load_model(cls, arch_fn, True)
+    x = weights.make_input((2, 3, 300, 25, 2), seed=11)
+    with torch.no_grad():
+        h = regular.pooled_sequence(x, sd, arch)
+        h = torch.nn.functional.avg_pool1d(h, arch.pool_size, stride=1, padding=arch.pool_padding)
+        want = torch.einsum("kc,nct->nkt", sd["fc.weight"], h) + sd["fc.bias"][None, :, None]
+    got = m.forward_steps(x.to(DEV), pad_end=True)
+    assert m.device_error() == 0
+    if want.shape[2] == 1:
+        want = want[:, :, 0]
+    assert tuple(got.shape) == tuple(want.shape), (tag, tuple(got.shape), tuple(want.shape))
+    scale = max(1.0, float(want.abs().max()) / 16.0)
+    assert float((got.cpu() - want).abs().max()) <= 1e-3 * scale
+    assert torch.equal(got.cpu().argmax(1), want.argmax(1))
