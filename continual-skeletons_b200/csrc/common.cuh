@@ -12,8 +12,18 @@
 namespace cosk {
 
 constexpr int kTileRows = 128;   // UMMA M: token rows per tile (only skel_per_tile*V of them are valid)
-constexpr int kRingSlots = 9;    // temporal ring: 8 history frames + the frame being written
-constexpr int kOutSlots = 5;     // block-output ring: newest + 4 delayed (residual alignment)
+constexpr int kRingSlots = 9;    // temporal ring, per-step stepping: 8 history frames + the frame being written
+constexpr int kOutSlots = 5;     // block-output ring, per-step stepping: newest + 4 delayed (residual alignment)
+// With a time chunk of Tc > 1 frames (cosk_set_batch_ex) the rings hold 8 + Tc and 4 + Tc slots, so that a whole chunk of
+// one block's executions can be in flight before the next block starts (module-by-module over time, as the library's
+// forward_steps runs, models/base.py:187-190).
+
+// Time-batched launches: one launch covers n_frames consecutive executions of a kernel and its work items become
+// (frame, tile) pairs.  Frame f of the launch lives in ring slot (slot0 + f * step) % slots.
+struct RingWalk {
+  int slot0 = 0, step = 1, slots = 1;
+  __host__ __device__ __forceinline__ int slot(int f) const { return (slot0 + f * step) % slots; }
+};
 constexpr int kTaps = 9;         // temporal kernel size (models/base.py:284,310 in the reference)
 constexpr int kResDelay = 4;     // every residual kind reads the block input of 4 executions ago
 

@@ -28,6 +28,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// ring slot of frame n (frames before the start of the stream, n < 0, map to slots that are still zero)
+inline int mod_slot(long long n, int slots) { return (int)(((n % slots) + slots) % slots); }
 
 struct ActBuf {  // token-major split-bf16 activation ring: [slots][plane hi/lo][t_alloc][cs]
   __nv_bfloat16 *ptr = nullptr;
@@ -39,6 +41,7 @@ struct ActBuf {  // token-major split-bf16 activation ring: [slots][plane hi/lo]
   __nv_bfloat16 *hi(int slot) const { return ptr + (size_t)slot * 2 * t_alloc * cs; }
   __nv_bfloat16 *lo(int slot) const { return hi(slot) + (size_t)t_alloc * cs; }
   long long row_hi(int slot) const { return (long long)slot * 2 * t_alloc; }
+  long long slot_elems() const { return 2 * t_alloc * cs; }
 };
 
 struct BlockW {
@@ -138,6 +141,8 @@ struct cosk_model {
   bool prepared = false;
   // state
   long long n_streams = 0, n_tokens = 0, t_alloc = 0;
+  int tchunk = 1;                    // time chunk: frames of one block processed per launch by cosk_steps (cosk_set_batch_ex)
+  int R = kRingSlots, Ro = kOutSlots;  // slots of the temporal rings (8 + tchunk) and of the input / block-output rings (4 + tchunk)
   int skel_per_tile = 0, tile_tokens = 0, n_tiles = 0;
   ActBuf xin;
   float *d_pool_ring = nullptr;
@@ -810,7 +815,7 @@ TcTcnArgs make_tcn_args(cosk_model *m, int i, const ActBuf &in, int res_slot, lo
   a.tm_ring = b.ring.map;
   a.tm_res = b.tcn_res_kblock ? in.map : b.ring.map;
   a.tm_w = b.map_tcn_w;
-  for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
+  for (int k = 0; k < kTaps; ++k) a.tap_row[k] = (int)b.ring.row_hi(mod_slot(n - (kTaps - 1) + k, m->R));  // frame n-8+k
   a.res_row = (int)in.row_hi(res_slot);
   a.t_alloc = (int)m->t_alloc;
   a.n_taps = kTaps;
@@ -856,7 +861,7 @@ int run_tcn_gcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long 
   TcTcnArgs ta = make_tcn_args(m, i, in, res_slot, n, out_slot);
   // the graph conv of block i+1 reads the output slot written here and pushes into its own ring
   const long long n_next = nb.n_in;
-  TcGcnArgs ga = make_gcn_args(m, i + 1, b.out, out_slot, (int)(n_next % kRingSlots));
+  TcGcnArgs ga = make_gcn_args(m, i + 1, b.out, out_slot, (int)(n_next % m->R));
   ta.reverse = 0;  // tiles are produced first to last, the order in which the other role consumes them
   ta.tile_cnt = b.d_tile_cnt;
   ga.wait_cnt = b.d_tile_cnt;
@@ -1203,7 +1208,7 @@ int run_tcn(cosk_model *m, int i, const ActBuf &in, int res_slot, long long n, i
   int rc = prof_mark(m, 2, i, s);
   if (rc) return rc;
   int tap_slot[kTaps];
-  for (int k = 0; k < kTaps; ++k) tap_slot[k] = (int)((n + 1 + k) % kRingSlots);  // frame n-8+k
+  for (int k = 0; k < kTaps; ++k) tap_slot[k] = mod_slot(n - (kTaps - 1) + k, m->R);  // frame n-8+k
   if (b.tc_tcn) {
     TcTcnArgs a = make_tcn_args(m, i, in, res_slot, n, out_slot);
     const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
@@ -1262,7 +1267,7 @@ int run_block64(cosk_model *m, int i, const ActBuf &in, int in_slot, long long n
   a.n_parts = b.gcnp_parts;
   a.x_row = (int)in.row_hi(in_slot);
   a.res_row = fire ? (int)in.row_hi(res_slot) : 0;
-  for (int k = 0; k < kTaps - 1; ++k) a.tap_row[k] = (int)b.ring.row_hi((int)((n + 1 + k) % kRingSlots));  // frame n-8+k
+  for (int k = 0; k < kTaps - 1; ++k) a.tap_row[k] = (int)b.ring.row_hi(mod_slot(n - (kTaps - 1) + k, m->R));  // frame n-8+k
   a.t_alloc = (int)m->t_alloc;
   a.with_tcn = fire ? 1 : 0;
   a.V = m->cfg.vertices;
@@ -1273,7 +1278,7 @@ int run_block64(cosk_model *m, int i, const ActBuf &in, int in_slot, long long n
   a.mix_src = b.d_mix_src;
   a.mix_val = b.d_mix_val;
   a.gbias = b.d_gcn_b;
-  const int ring_slot = (int)(n % kRingSlots);
+  const int ring_slot = (int)(n % m->R);
   a.g_hi = b.ring.hi(ring_slot);
   a.g_lo = b.ring.lo(ring_slot);
   a.cs_g = b.ring.cs;
@@ -1312,7 +1317,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   const cosk_config &c = m->cfg;
   int rc;
   // input frame -> token rows (data_bn folded in)
-  const int xslot = (int)(m->frame % kOutSlots);
+  const int xslot = (int)(m->frame % m->Ro);
   if ((rc = prof_mark(m, 0, -1, s))) return rc;
   if (!flush) {
     const long long total = m->n_tokens * m->xin.cs;
@@ -1320,7 +1325,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     const long long blocks = (total + threads - 1) / threads;
     CK(launch_k(m, k_input, dim3((unsigned)blocks), dim3(threads), 0, s, x, (long long)nc_stride, c.c_in, c.vertices, c.persons,
                 (const float *)(c.data_bn ? m->d_bn_scale : nullptr), (const float *)(c.data_bn ? m->d_bn_shift : nullptr),
-                m->xin.hi(xslot), m->xin.lo(xslot), m->xin.cs, m->n_tokens));
+                m->xin.hi(xslot), m->xin.lo(xslot), m->xin.cs, m->n_tokens, 0LL, RingWalk(), 0LL));
     m->launches++;
   }
   const ActBuf *in = &m->xin;
@@ -1337,24 +1342,24 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
     BlockW &b = m->blk[i];
     const cosk_block_cfg &bc = c.blocks[i];
     const long long n = b.n_in;  // index of this input == index of the predecessor's emission
-    const int in_slot = (int)(n % kOutSlots);
+    const int in_slot = (int)(n % m->Ro);
     const bool fire = tcn_fires(n, c.padding, bc.stride);
     const bool zero_in = flush && i == enter;  // a zero frame enters the temporal conv directly
     const bool fused = b.fuse && !gcn_done && in->has_map && !zero_in;
     if (zero_in) {
-      const int rs = (int)(n % kRingSlots);
+      const int rs = (int)(n % m->R);
       CK(cudaMemsetAsync(b.ring.hi(rs), 0, (size_t)2 * b.ring.t_alloc * b.ring.cs * sizeof(__nv_bfloat16), s));
     } else if (fused) {
-      const int res_slot = fire ? (int)((n - kResDelay) % kOutSlots) : 0;
-      if ((rc = run_block64(m, i, *in, in_slot, n, fire, res_slot, (int)(b.n_out % kOutSlots), s))) return rc;
+      const int res_slot = fire ? (int)((n - kResDelay) % m->Ro) : 0;
+      if ((rc = run_block64(m, i, *in, in_slot, n, fire, res_slot, (int)(b.n_out % m->Ro), s))) return rc;
       if (fire) b.n_out++;
-    } else if (!gcn_done && (rc = run_gcn(m, i, *in, in_slot, (int)(n % kRingSlots), s))) {
+    } else if (!gcn_done && (rc = run_gcn(m, i, *in, in_slot, (int)(n % m->R), s))) {
       return rc;
     }
     gcn_done = false;
     if (fire && !fused) {
-      const int res_slot = (int)((n - kResDelay) % kOutSlots);  // n >= first >= 4
-      const int out_slot = (int)(b.n_out % kOutSlots);
+      const int res_slot = (int)((n - kResDelay) % m->Ro);  // n >= first >= 4
+      const int out_slot = (int)(b.n_out % m->Ro);
       if (can_merge(m, i)) {
         if ((rc = run_tcn_gcn(m, i, *in, res_slot, n, out_slot, s))) return rc;
         gcn_done = true;
@@ -1372,7 +1377,7 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   if (head_flush && c.classes == 0) alive = false;  // nothing to flush without a pooling window
   if (alive) {
     const BlockW &last = m->blk[c.n_blocks - 1];
-    const int slot = (int)(((last.n_out > 0 ? last.n_out : 1) - 1) % kOutSlots);
+    const int slot = (int)(((last.n_out > 0 ? last.n_out : 1) - 1) % m->Ro);
     if (c.classes > 0) {
       emit = head_fires(m->pool_n, c.pool_size, c.pool_padding) ? 1 : 0;
       if ((rc = prof_mark(m, 3, -1, s))) return rc;
@@ -1409,6 +1414,235 @@ int step_impl(cosk_model *m, const float *x, long long nc_stride, float *out, in
   m->last_flags[c.n_blocks] = emit;
   if (!flush) m->frame++;
   if (emitted) *emitted = emit;
+  return COSK_OK;
+}
+
+// ---- time-batched stepping (cosk_steps with a time chunk > 1) ------------------------------------------------------
+// The stack is walked module by module over a chunk of F0 <= tchunk frames, one launch per kernel and chunk; the work items
+// of a launch are (frame, tile) pairs and every frame's ring slots follow from a RingWalk.  Available when every block runs
+// on the tensor-core CoST-GCN kernels (k_tc_gcn, k_gcn_small for the first layer, k_tc_tcn / k_tc_tcn2).
+bool batched_ok(const cosk_model *m) {
+  if (m->tchunk <= 1 || m->cfg.path != COSK_PATH_AUTO || m->merge || m->d_trace) return false;
+  for (int i = 0; i < m->cfg.n_blocks; ++i) {
+    const cosk_block_cfg &bc = m->cfg.blocks[i];
+    const BlockW &b = m->blk[i];
+    if (bc.gconv != COSK_GCONV_PLAIN || !b.tc_tcn) return false;
+    const int res_conv = bc.cin != bc.cout ? 1 : 0;
+    const bool small = bc.cin <= 8 && res_conv && bc.cout % 32 == 0 && (3 + res_conv) * bc.cin <= kSmallKMax;
+    if (!((b.tc_gcn && !b.tc_gcnp) || small)) return false;
+  }
+  return true;
+}
+
+int steps_chunk(cosk_model *m, const float *x, long long nc_stride, long long x_frame_stride, int F0, float *out, long long out_stride,
+                int32_t max_out, int32_t *cnt, cudaStream_t s) {
+  const cosk_config &c = m->cfg;
+  const int slot_rows = (int)(2 * m->t_alloc);
+  int rc;
+  if ((rc = prof_mark(m, 0, -1, s))) return rc;
+  {
+    const long long total = m->n_tokens * m->xin.cs;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    RingWalk ow;
+    ow.slot0 = mod_slot(m->frame, m->Ro);
+    ow.step = 1;
+    ow.slots = m->Ro;
+    CK(launch_k(m, k_input, dim3((unsigned)blocks, (unsigned)F0), dim3(threads), 0, s, x, (long long)nc_stride, c.c_in, c.vertices, c.persons,
+                (const float *)(c.data_bn ? m->d_bn_scale : nullptr), (const float *)(c.data_bn ? m->d_bn_shift : nullptr),
+                m->xin.hi(0), m->xin.lo(0), m->xin.cs, m->n_tokens, x_frame_stride, ow, m->xin.slot_elems()));
+    m->launches++;
+  }
+  const ActBuf *in = &m->xin;
+  int F = F0;  // executions of the current block in this chunk == emissions of its predecessor
+  for (int i = 0; i < c.n_blocks; ++i) {
+    BlockW &b = m->blk[i];
+    const cosk_block_cfg &bc = c.blocks[i];
+    m->last_flags[i] = 0;
+    if (F == 0) {
+      in = &b.out;
+      continue;
+    }
+    const long long n0 = b.n_in;
+    const int first = (kTaps - 1) - c.padding;
+    // firing executions among n0 .. n0+F-1: n >= first and (n - first) % stride == 0
+    long long nf = n0 < first ? first : n0 + ((first - n0) % bc.stride + bc.stride) % bc.stride;
+    const int F_out = nf <= n0 + F - 1 ? (int)((n0 + F - 1 - nf) / bc.stride) + 1 : 0;
+    const long long out0 = b.n_out;
+    RingWalk in_walk, ring_walk, tap_walk, res_walk, out_walk;
+    in_walk.slot0 = mod_slot(n0, m->Ro), in_walk.step = 1, in_walk.slots = m->Ro;
+    ring_walk.slot0 = mod_slot(n0, m->R), ring_walk.step = 1, ring_walk.slots = m->R;
+    tap_walk.slot0 = mod_slot(nf - (kTaps - 1), m->R), tap_walk.step = bc.stride, tap_walk.slots = m->R;
+    res_walk.slot0 = mod_slot(nf - kResDelay, m->Ro), res_walk.step = bc.stride, res_walk.slots = m->Ro;
+    out_walk.slot0 = mod_slot(out0, m->Ro), out_walk.step = 1, out_walk.slots = m->Ro;
+    // (The fused block kernel is not used here: frame n's temporal conv reads the graph-conv outputs of frames n-8 .. n-1,
+    // which a launch covering many frames would produce concurrently.  The chunk runs graph conv and temporal conv of such a
+    // block as two launches -- module by module, every frame of the first complete before the second starts.)
+    {
+      // graph conv over the F executions
+      if ((rc = prof_mark(m, 1, i, s))) return rc;
+      if (b.tc_gcn) {
+        TcGcnArgs a = make_gcn_args(m, i, *in, in_walk.slot0, ring_walk.slot0);
+        if (F > 1) {
+          a.n_frames = F;
+          a.slot_rows = slot_rows;
+          a.in_walk = in_walk;
+          a.out_walk = ring_walk;
+          a.in_slot_elems = in->slot_elems();
+          a.out_slot_elems = b.ring.slot_elems();
+          a.x_row = 0;
+          a.epi.y_hi = b.ring.hi(0);
+          a.epi.y_lo = b.ring.lo(0);
+          if (a.epi.r_hi != nullptr) {
+            a.epi.r_hi = in->hi(0);
+            a.epi.r_lo = in->lo(0);
+          }
+        }
+        const bool one_kb = bc.cin == kBK && m->gcn_single_stage;
+        const int items = m->n_tiles * F;
+        const int grid = items < m->num_sms ? items : m->num_sms;
+        if (b.gcn_parts == 4) {
+          if (one_kb) CK(launch_k(m, k_tc_gcn<4, 1, false>, dim3(grid), dim3(512), TcGcnCfg<4, 1>::kSmemBytes, s, a));
+          else CK(launch_k(m, k_tc_gcn<4, 2, false>, dim3(grid), dim3(512), TcGcnCfg<4, 2>::kSmemBytes, s, a));
+        } else {
+          if (one_kb) CK(launch_k(m, k_tc_gcn<3, 1, false>, dim3(grid), dim3(512), TcGcnCfg<3, 1>::kSmemBytes, s, a));
+          else CK(launch_k(m, k_tc_gcn<3, 2, false>, dim3(grid), dim3(512), TcGcnCfg<3, 2>::kSmemBytes, s, a));
+        }
+      } else {  // narrow first layer
+        GcnArgs a;
+        a.x_hi = in->hi(0);
+        a.x_lo = in->lo(0);
+        a.cs_in = in->cs;
+        a.cin = bc.cin;
+        a.y_hi = b.ring.hi(0);
+        a.y_lo = b.ring.lo(0);
+        a.cs_out = b.ring.cs;
+        a.cout = bc.cout;
+        a.w = b.d_gcn_w;
+        a.bias = b.d_gcn_b;
+        a.res_conv = 1;
+        a.res_identity = 0;
+        a.mix_ptr = b.d_mix_ptr;
+        a.mix_src = b.d_mix_src;
+        a.mix_val = b.d_mix_val;
+        a.V = c.vertices;
+        a.n_tokens = m->n_tokens;
+        a.tile_tokens = m->tile_tokens;
+        a.dense = nullptr;
+        a.dense_ld = a.dense_vp = 0;
+        a.in_walk = in_walk;
+        a.out_walk = ring_walk;
+        a.in_slot_elems = in->slot_elems();
+        a.out_slot_elems = b.ring.slot_elems();
+        const int K = 4 * bc.cin;
+        CK(launch_k(m, k_gcn_small, dim3(m->n_tiles, F), dim3(256), (size_t)(K + 1) * bc.cout * sizeof(float), s, a));
+      }
+      m->launches++;
+      // temporal conv over the F_out firing executions
+      if (F_out > 0) {
+        if ((rc = prof_mark(m, 2, i, s))) return rc;
+        TcTcnArgs a = make_tcn_args(m, i, *in, res_walk.slot0, nf, out_walk.slot0);
+        if (F_out > 1) {
+          a.n_frames = F_out;
+          a.slot_rows = slot_rows;
+          a.tap_walk = tap_walk;
+          a.res_walk = res_walk;
+          a.out_walk = out_walk;
+          a.out_slot_elems = b.out.slot_elems();
+          a.res_slot_elems = in->slot_elems();
+          a.epi.y_hi = b.out.hi(0);
+          a.epi.y_lo = b.out.lo(0);
+          if (a.epi.r_hi != nullptr) {
+            a.epi.r_hi = in->hi(0);
+            a.epi.r_lo = in->lo(0);
+          }
+        }
+        const bool pair = m->n_tiles >= 2 && (m->pair_mask & (bc.cout == 64 ? 1 : bc.cout == 128 ? 2 : 4));
+        if (pair) {
+          if (bc.cout > 128) a.tm_w = b.map_tcn_w_half;
+          const int n_pairs = (m->n_tiles + 1) / 2 * F_out;
+          const int max_clusters = m->num_sms / 2;
+          const int grid = 2 * (n_pairs < max_clusters ? n_pairs : max_clusters);
+          if (bc.cout == 64) CK(launch_k(m, k_tc_tcn2<64>, dim3(grid), dim3(256), TcTcn2Cfg<64>::kSmemBytes, s, a));
+          else if (bc.cout == 128) CK(launch_k(m, k_tc_tcn2<128>, dim3(grid), dim3(256), TcTcn2Cfg<128>::kSmemBytes, s, a));
+          else CK(launch_k(m, k_tc_tcn2<256>, dim3(grid), dim3(256), TcTcn2Cfg<256>::kSmemBytes, s, a));
+        } else {
+          const int items = m->n_tiles * F_out;
+          const int grid = items < m->num_sms ? items : m->num_sms;
+          if (bc.cout == 64) CK(launch_k(m, k_tc_tcn<64>, dim3(grid), dim3(256), TcTcnCfg<64>::kSmemBytes, s, a));
+          else if (bc.cout == 128) CK(launch_k(m, k_tc_tcn<128>, dim3(grid), dim3(256), TcTcnCfg<128>::kSmemBytes, s, a));
+          else CK(launch_k(m, k_tc_tcn<256>, dim3(grid), dim3(256), TcTcnCfg<256>::kSmemBytes, s, a));
+        }
+        m->launches++;
+      }
+    }
+    // did the block fire on the LAST frame of the chunk?  (schedule parity is defined per frame)
+    m->last_flags[i] = (F_out > 0 && nf + (long long)(F_out - 1) * bc.stride == n0 + F - 1) ? 1 : 0;
+    b.n_in += F;
+    b.n_out += F_out;
+    F = F_out;
+    in = &b.out;
+  }
+  // head over the F emissions of the last block
+  int emit_last = 0;
+  if (F > 0) {
+    const BlockW &last = m->blk[c.n_blocks - 1];
+    const long long o0 = last.n_out - F;  // index of the first of these emissions
+    if (c.classes > 0) {
+      if ((rc = prof_mark(m, 3, -1, s))) return rc;
+      const long long first_emit_n = (long long)c.pool_size - 1 - c.pool_padding;
+      const int skip = (int)std::min<long long>(std::max<long long>(first_emit_n - m->pool_n, 0), F);  // frames before the first logits
+      const int n_emit = F - skip;
+      const int32_t room = *cnt < max_out ? max_out - *cnt : 0;
+      HeadArgs h;
+      h.y_hi = last.out.hi(0);
+      h.y_lo = last.out.lo(0);
+      h.cs = last.out.cs;
+      h.c = last.out.c;
+      h.V = c.vertices;
+      h.S = c.persons;
+      h.ring = m->d_pool_ring;
+      h.sum = m->d_pool_sum;
+      h.slot = (int)(m->pool_n % c.pool_size);
+      h.P = c.pool_size;
+      h.n_streams = m->n_streams;
+      h.emit = 0;
+      h.w = m->d_fc_w;
+      h.b = m->d_fc_b;
+      h.classes = c.classes;
+      h.out = out + (long long)(*cnt < max_out ? *cnt : max_out - 1) * out_stride;
+      h.n_frames = F;
+      h.in_walk.slot0 = mod_slot(o0, m->Ro), h.in_walk.step = 1, h.in_walk.slots = m->Ro;
+      h.in_slot_elems = last.out.slot_elems();
+      h.first_emit = skip;
+      h.out_stride = n_emit <= room ? out_stride : 0;  // more emissions than room: they all land in the last slot
+      if (F == 1) {  // single frame: plain per-step arguments
+        h.y_hi += (long long)h.in_walk.slot0 * h.in_slot_elems;
+        h.y_lo += (long long)h.in_walk.slot0 * h.in_slot_elems;
+        h.emit = n_emit;
+      }
+      CK(launch_k(m, k_head, dim3((unsigned)((m->n_streams + kHeadStreams - 1) / kHeadStreams)), dim3(256 * kHeadStreams),
+                  (size_t)kHeadStreams * (2 * last.out.cs + last.out.c) * sizeof(float), s, h));
+      m->launches++;
+      m->pool_n += F;
+      *cnt += n_emit;
+      emit_last = n_emit > 0 ? 1 : 0;
+    } else {
+      for (int f = 0; f < F; ++f) {
+        const int slot = mod_slot(o0 + f, m->Ro);
+        const long long total = m->n_tokens * last.out.c;
+        float *dst = out + (long long)(*cnt < max_out ? *cnt : max_out - 1) * out_stride;
+        CK(launch_k(m, k_read_block, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, (const __nv_bfloat16 *)last.out.hi(slot),
+                    (const __nv_bfloat16 *)last.out.lo(slot), last.out.cs, last.out.c, c.vertices, m->n_tokens, dst));
+        m->launches++;
+        *cnt += 1;
+      }
+      emit_last = 1;
+    }
+  }
+  if ((rc = prof_mark(m, -1, -1, s))) return rc;
+  m->last_flags[c.n_blocks] = (emit_last && m->last_flags[c.n_blocks - 1]) ? 1 : 0;
+  m->frame += F0;
   return COSK_OK;
 }
 
@@ -1593,9 +1827,14 @@ int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t
   return COSK_OK;
 }
 
-int cosk_set_batch(cosk_model *m, int64_t n_streams) {
-  if (!m || n_streams < 1) return COSK_ERR_ARG;
+int cosk_set_batch(cosk_model *m, int64_t n_streams) { return cosk_set_batch_ex(m, n_streams, 1); }
+
+int cosk_set_batch_ex(cosk_model *m, int64_t n_streams, int32_t time_chunk) {
+  if (!m || n_streams < 1 || time_chunk < 1 || time_chunk > 4096) return COSK_ERR_ARG;
   DeviceGuard guard_(m->cfg.device);
+  m->tchunk = time_chunk;
+  m->R = (kRingSlots - 1) + time_chunk;
+  m->Ro = (kOutSlots - 1) + time_chunk;
   if (!m->prepared) {
     int rc = prepare(m);
     if (rc) return rc;
@@ -1611,12 +1850,12 @@ int cosk_set_batch(cosk_model *m, int64_t n_streams) {
   m->n_tiles = (int)((skel + m->skel_per_tile - 1) / m->skel_per_tile);
   // +1 tile: with an odd tile count the second CTA of the last pair walks a phantom tile (loads only)
   m->t_alloc = round_up((int)((long long)(m->n_tiles + 1) * m->tile_tokens + (kTileRows - m->tile_tokens)), 8);
-  if ((long long)kRingSlots * 2 * m->t_alloc > 0x7fffffffLL) return fail(m, COSK_ERR_ARG, "too many streams for 32-bit rows");
-  int rc = alloc_act(m, m->xin, kOutSlots, c.c_in);
+  if ((long long)m->R * 2 * m->t_alloc > 0x7fffffffLL) return fail(m, COSK_ERR_ARG, "too many streams (x time chunk) for 32-bit rows");
+  int rc = alloc_act(m, m->xin, m->Ro, c.c_in);
   if (rc) return rc;
   for (int i = 0; i < c.n_blocks; ++i) {
-    if ((rc = alloc_act(m, m->blk[i].ring, kRingSlots, c.blocks[i].cout))) return rc;
-    if ((rc = alloc_act(m, m->blk[i].out, kOutSlots, c.blocks[i].cout))) return rc;
+    if ((rc = alloc_act(m, m->blk[i].ring, m->R, c.blocks[i].cout))) return rc;
+    if ((rc = alloc_act(m, m->blk[i].out, m->Ro, c.blocks[i].cout))) return rc;
     CK(cudaMalloc(&m->blk[i].d_tile_cnt, sizeof(unsigned int) * (size_t)(m->n_tiles + 2)));
   }
   if (c.classes > 0) {
@@ -1729,7 +1968,22 @@ int cosk_steps_ex(cosk_model *m, const float *x_dev, int32_t T, float *out_dev, 
   DeviceGuard guard_(m->cfg.device);
   const long long frame_elems = (long long)m->cfg.vertices * m->cfg.persons;
   int32_t cnt = 0;
-  for (int t = 0; t < T; ++t) {
+  int t_start = 0;
+  if (batched_ok(m)) {
+    // module by module over chunks of up to tchunk frames, one launch per kernel and chunk
+    for (int t0 = 0; t0 < T; t0 += m->tchunk) {
+      const int F0 = std::min(m->tchunk, T - t0);
+      rc = steps_chunk(m, x_dev + t0 * frame_elems, (long long)T * frame_elems, frame_elems, F0, out_dev, out_stride, max_out, &cnt,
+                       (cudaStream_t)stream);
+      if (rc) {
+        m->failed = true;
+        return rc;
+      }
+    }
+    if (cnt > 0 && m->h_dbg) cudaMemcpyAsync(m->h_dbg, m->d_dbg, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    t_start = T;
+  }
+  for (int t = t_start; t < T; ++t) {
     int32_t em = 0;
     // once max_out emissions are stored, later ones land in the last slot
     const int32_t dst = cnt < max_out ? cnt : max_out - 1;
@@ -1778,7 +2032,7 @@ int cosk_read_block(cosk_model *m, int32_t block, float *dst_dev, void *stream) 
   const BlockW &b = m->blk[block];
   if (b.n_out == 0) return fail(m, COSK_ERR_STATE, "block %d has not emitted yet", block);
   DeviceGuard guard_(m->cfg.device);
-  const int slot = (int)((b.n_out - 1) % kOutSlots);
+  const int slot = (int)((b.n_out - 1) % m->Ro);
   const long long total = m->n_tokens * b.out.c;
   CK(launch_k(m, k_read_block, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
               (const __nv_bfloat16 *)b.out.hi(slot), (const __nv_bfloat16 *)b.out.lo(slot), b.out.cs, b.out.c, m->cfg.vertices,

@@ -11,13 +11,23 @@ namespace cosk {
 // input: one frame (N, C, V, S) fp32 -> token-major split-bf16 rows, with data_bn folded in.
 // Reference: reshape1 / data_bn / reshape2, models/base.py:73-82 (feature f = s*V*C + v*C + c).
 // ---------------------------------------------------------------------------------------------
+// Time-batched launch: blockIdx.y = frame f of the chunk, read at x + f * x_frame_stride and written to slot ow.slot(f)
+// of the input ring (hi / lo then point at slot 0; a single-frame launch passes the slot's own pointers and a unit walk).
 __global__ void k_input(const float *__restrict__ x, long long nc_stride, int C, int V, int S,
                         const float *__restrict__ scale, const float *__restrict__ shift,
-                        __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cs, long long n_tokens) {
+                        __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int cs, long long n_tokens,
+                        long long x_frame_stride, RingWalk ow, long long slot_elems) {
   pdl_trigger();
   pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_tokens * cs) return;
+  {
+    const int f = (int)blockIdx.y;
+    x += (long long)f * x_frame_stride;
+    const long long o = (long long)ow.slot(f) * slot_elems;
+    hi += o;
+    lo += o;
+  }
   long long tok = idx / cs;
   int c = (int)(idx % cs);
   float val = 0.f;
@@ -113,6 +123,10 @@ struct GcnArgs {
   // row of output token w, partition p, source vertex v: dense[w*dense_ld + p*dense_vp + v]
   const float *dense;
   int dense_ld, dense_vp;
+  // time-batched launch of k_gcn_small (blockIdx.y = frame): input slot in_walk.slot(f), ring slot out_walk.slot(f);
+  // x_* / y_* then point at slot 0 of their rings
+  RingWalk in_walk, out_walk;
+  long long in_slot_elems = 0, out_slot_elems = 0;
 };
 
 // Graph convolution of one frame: z = sum_i W_i (x A_i) ; BN ; + gcn_residual(x) ; ReLU
@@ -205,6 +219,14 @@ __global__ void __launch_bounds__(256) k_gcn_simt(GcnArgs a) {
 constexpr int kSmallKMax = 32;
 
 __global__ void __launch_bounds__(256) k_gcn_small(GcnArgs a) {
+  {
+    const int f = (int)blockIdx.y;
+    const long long i = (long long)a.in_walk.slot(f) * a.in_slot_elems, o = (long long)a.out_walk.slot(f) * a.out_slot_elems;
+    a.x_hi += i;
+    a.x_lo += i;
+    a.y_hi += o;
+    a.y_lo += o;
+  }
   __shared__ float xs[kTileRows][8 + 1];             // normalised input rows
   __shared__ __align__(16) float xa[kSmallKMax][kTileRows + 4];  // k-major [part-major mixed inputs | raw input]
   extern __shared__ __align__(16) float w_s[];       // [K][cout] k-major weights, then bias[cout]
@@ -753,6 +775,13 @@ struct HeadArgs {
   const float *w, *b;  // [classes][c], [classes]
   int classes;
   float *out;  // [N][classes]
+  // time-batched launch: n_frames pooled frames in sequence (slot in_walk.slot(f) of the last block's output ring; y_* then
+  // point at slot 0), window slot (slot + f) % P, emission from frame first_emit on, emission j written at out + j * out_stride
+  int n_frames = 1;
+  RingWalk in_walk;
+  long long in_slot_elems = 0;
+  int first_emit = 0;
+  long long out_stride = 0;
 };
 
 constexpr int kHeadStreams = 4;  // streams per CTA (256 threads each): the FC weight rows are fetched once for all of them
@@ -768,62 +797,74 @@ __global__ void __launch_bounds__(256 * kHeadStreams) k_head(HeadArgs a) {
   const long long n = n0 + g;
   const bool live = n < a.n_streams;
   const int half = tid >> 7, t128 = tid & 127;
-  if (live && a.y_hi == nullptr) {
-    // end-of-sequence flush of the pooling window (pad_end): a zero vector enters (co.AvgPool1d's end padding)
-    for (int c = t128 + 128 * half; c < 2 * a.cs; c += 256) part[c] = 0.f;
-  } else if (live) {
-    const long long tok0 = n * a.S * a.V;
-    // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
-    for (int cp = t128; cp < a.cs / 2; cp += 128) {
-      float t0 = 0.f, t1 = 0.f;
-      for (int s = half; s < a.S; s += 2) {
-        float p0 = 0.f, p1 = 0.f;
-        const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
+  for (int f = 0; f < a.n_frames; ++f) {
+    const bool emit = a.n_frames == 1 ? a.emit != 0 : f >= a.first_emit;
+    const int wslot = (a.slot + f) % a.P;
+    const __nv_bfloat16 *y_hi = a.y_hi, *y_lo = a.y_lo;
+    if (a.n_frames > 1) {
+      const long long o = (long long)a.in_walk.slot(f) * a.in_slot_elems;
+      y_hi += o;
+      y_lo += o;
+    }
+    if (live && y_hi == nullptr) {
+      // end-of-sequence flush of the pooling window (pad_end): a zero vector enters (co.AvgPool1d's end padding)
+      for (int c = t128 + 128 * half; c < 2 * a.cs; c += 256) part[c] = 0.f;
+    } else if (live) {
+      const long long tok0 = n * a.S * a.V;
+      // two thread halves split the skeletons of the stream; each thread owns a bf16x2 channel pair
+      for (int cp = t128; cp < a.cs / 2; cp += 128) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int s = half; s < a.S; s += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
 #pragma unroll 5
-        for (int v = 0; v < a.V; ++v) {
-          const uint32_t h = *reinterpret_cast<const uint32_t *>(a.y_hi + base + (long long)v * a.cs);
-          const uint32_t l = *reinterpret_cast<const uint32_t *>(a.y_lo + base + (long long)v * a.cs);
-          p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
-          p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
+          for (int v = 0; v < a.V; ++v) {
+            const uint32_t h = *reinterpret_cast<const uint32_t *>(y_hi + base + (long long)v * a.cs);
+            const uint32_t l = *reinterpret_cast<const uint32_t *>(y_lo + base + (long long)v * a.cs);
+            p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
+            p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
+          }
+          t0 += p0 / (float)a.V;
+          t1 += p1 / (float)a.V;
         }
-        t0 += p0 / (float)a.V;
-        t1 += p1 / (float)a.V;
+        part[half * a.cs + 2 * cp] = t0;
+        part[half * a.cs + 2 * cp + 1] = t1;
       }
-      part[half * a.cs + 2 * cp] = t0;
-      part[half * a.cs + 2 * cp + 1] = t1;
     }
-  }
-  __syncthreads();
-  if (live) {
-    for (int c = tid; c < a.c; c += 256) {
-      const float h = (part[c] + part[a.cs + c]) / (float)a.S;
-      const long long ri = ((long long)a.slot * a.n_streams + n) * a.c + c;
-      const float old = a.ring[ri];
-      a.ring[ri] = h;
-      const double s2 = a.sum[n * a.c + c] + ((double)h - (double)old);
-      a.sum[n * a.c + c] = s2;
-      mean_s[g * a.c + c] = (float)(s2 / (double)a.P);
+    __syncthreads();
+    if (live) {
+      for (int c = tid; c < a.c; c += 256) {
+        const float h = (part[c] + part[a.cs + c]) / (float)a.S;
+        const long long ri = ((long long)wslot * a.n_streams + n) * a.c + c;
+        const float old = a.ring[ri];
+        a.ring[ri] = h;
+        const double s2 = a.sum[n * a.c + c] + ((double)h - (double)old);
+        a.sum[n * a.c + c] = s2;
+        mean_s[g * a.c + c] = (float)(s2 / (double)a.P);
+      }
     }
-  }
-  if (!a.emit) return;
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int k = warp; k < a.classes; k += nw) {
-    float p[kHeadStreams];
+    __syncthreads();
+    if (!emit) continue;
+    float *out = a.out + (a.n_frames == 1 ? 0 : (long long)(f - a.first_emit) * a.out_stride);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int k = warp; k < a.classes; k += nw) {
+      float p[kHeadStreams];
 #pragma unroll
-    for (int j = 0; j < kHeadStreams; ++j) p[j] = 0.f;
-    for (int c = lane; c < a.c; c += 32) {
-      const float wv = a.w[(long long)k * a.c + c];
+      for (int j = 0; j < kHeadStreams; ++j) p[j] = 0.f;
+      for (int c = lane; c < a.c; c += 32) {
+        const float wv = a.w[(long long)k * a.c + c];
 #pragma unroll
-      for (int j = 0; j < kHeadStreams; ++j) p[j] = fmaf(wv, mean_s[j * a.c + c], p[j]);
+        for (int j = 0; j < kHeadStreams; ++j) p[j] = fmaf(wv, mean_s[j * a.c + c], p[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kHeadStreams; ++j) {
+        float v = p[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && n0 + j < a.n_streams) out[(n0 + j) * a.classes + k] = v + a.b[k];
+      }
     }
-#pragma unroll
-    for (int j = 0; j < kHeadStreams; ++j) {
-      float v = p[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && n0 + j < a.n_streams) a.out[(n0 + j) * a.classes + k] = v + a.b[k];
-    }
+    __syncthreads();  // mean_s / part are rewritten by the next frame
   }
 }
 

@@ -166,7 +166,36 @@ struct TcTcnArgs {
   unsigned int *tile_cnt;  // optional [n_tiles] counters: each epilogue warp adds 1 once its rows of a tile are stored
                            // (release), so a graph-conv role of the same launch can start on that tile
   unsigned int *dbg;
+  // time-batched launch (n_frames > 1): frame f reads taps from slots (tap_walk.slot(f) + k) % tap_walk.slots of the temporal
+  // ring, the delayed input from res_walk.slot(f) of the input ring, and writes out_walk.slot(f) of the output ring;
+  // epi.y_* / epi.r_* then point at slot 0 of their rings.  n_frames == 1: tap_row / res_row / epi as given.
+  int n_frames = 1;
+  int slot_rows = 0;  // rows per ring slot (2 * t_alloc)
+  RingWalk tap_walk, res_walk, out_walk;
+  long long out_slot_elems = 0, res_slot_elems = 0;
 };
+
+// rows and pointers of frame f of a (possibly time-batched) temporal-conv launch
+__device__ __forceinline__ int tcn_tap_row(const TcTcnArgs &a, int f, int tap) {
+  return a.n_frames == 1 ? a.tap_row[tap] : ((a.tap_walk.slot(f) + tap) % a.tap_walk.slots) * a.slot_rows;
+}
+__device__ __forceinline__ int tcn_res_row(const TcTcnArgs &a, int f) {
+  return a.n_frames == 1 ? a.res_row : a.res_walk.slot(f) * a.slot_rows;
+}
+__device__ __forceinline__ EpiArgs tcn_epi(const TcTcnArgs &a, int f) {
+  EpiArgs e = a.epi;
+  if (a.n_frames > 1) {
+    const long long o = (long long)a.out_walk.slot(f) * a.out_slot_elems;
+    e.y_hi += o;
+    e.y_lo += o;
+    if (e.r_hi != nullptr) {
+      const long long r = (long long)a.res_walk.slot(f) * a.res_slot_elems;
+      e.r_hi += r;
+      e.r_lo += r;
+    }
+  }
+  return e;
+}
 
 template <int COUT>
 struct TcTcnCfg {
@@ -236,6 +265,7 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const int nkb = a.n_taps * a.kb_per_tap + a.kb_res;
+  const int n_items = a.n_tiles * a.n_frames;  // (frame, tile) work items
 
   if (warp == 0) {
     if (lane == 0) {
@@ -244,8 +274,9 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
       const bool tr = a.trace != nullptr && cta == 0;
       unsigned long long tw = 0;
       const long long tstart = tr ? clock64() : 0;
-      for (int ti = cta; ok && ti < a.n_tiles; ti += ncta) {
-        const int tile = a.reverse ? cta + ncta * ((a.n_tiles - 1 - cta) / ncta) - (ti - cta) : ti;
+      for (int ti = cta; ok && ti < n_items; ti += ncta) {
+        const int vt = a.reverse ? cta + ncta * ((n_items - 1 - cta) / ncta) - (ti - cta) : ti;
+        const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
         const int tok0 = tile * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           const long long w0 = tr ? clock64() : 0;
@@ -260,11 +291,11 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
             const int tap = kb / a.kb_per_tap;
             tm = &a.tm_ring;
             c0 = (kb - tap * a.kb_per_tap) * kBK;
-            row = a.tap_row[tap] + tok0;
+            row = tcn_tap_row(a, fr, tap) + tok0;
           } else {
             tm = &a.tm_res;
             c0 = (kb - a.n_taps * a.kb_per_tap) * kBK;
-            row = a.res_row + tok0;
+            row = tcn_res_row(a, fr) + tok0;
           }
           // ring history and delayed residual are read once per step: stream them (evict-first) so the
           // frames written moments ago by the previous kernel stay in L2 until they are consumed
@@ -293,7 +324,7 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
       const bool tr = a.trace != nullptr && cta == 0;
       unsigned long long tw_ops = 0, tw_acc = 0;
       const long long tstart = tr ? clock64() : 0;
-      for (int tile = cta; ok && tile < a.n_tiles; tile += ncta, ++it) {
+      for (int tile = cta; ok && tile < n_items; tile += ncta, ++it) {
         const int acc = it & 1;
         const long long w0 = tr ? clock64() : 0;
         ok = ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1, a.dbg, kDbgMmaTmemEmpty | (unsigned)it);
@@ -330,8 +361,9 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
     const int q = warp & 3;
     bool ok = true;
     int it = 0;
-    for (int ti = cta; ok && ti < a.n_tiles; ti += ncta, ++it) {
-      const int tile = a.reverse ? cta + ncta * ((a.n_tiles - 1 - cta) / ncta) - (ti - cta) : ti;
+    for (int ti = cta; ok && ti < n_items; ti += ncta, ++it) {
+      const int vt = a.reverse ? cta + ncta * ((n_items - 1 - cta) / ncta) - (ti - cta) : ti;
+      const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
@@ -339,7 +371,8 @@ __device__ __forceinline__ void tcn_body(const TcTcnArgs &a, uint8_t *smem_raw, 
       const int row = q * 32 + lane;
       const long long tok = (long long)tile * a.tile_tokens + row;
       const bool valid = row < a.tile_tokens && tok < a.n_tokens;
-      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, a.epi, tok, valid);
+      const EpiArgs epi = tcn_epi(a, fr);
+      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, epi, tok, valid);
       ptx::tc_fence_before();
       if (a.tile_cnt != nullptr) __threadfence();  // this lane's output rows are visible device-wide ...
       __syncwarp();
@@ -457,14 +490,16 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   const int nkb = a.n_taps * a.kb_per_tap + a.kb_res;
-  const int n_pairs = (a.n_tiles + 1) / 2;
+  const int pairs_per_frame = (a.n_tiles + 1) / 2;      // tile pairs never straddle two frames of a time-batched launch
+  const int n_pairs = pairs_per_frame * a.n_frames;
 
   if (warp == 0) {
     if (lane == 0) {
       PipeState pa, pb;
       bool ok = true;
       for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters) {
-        const int pr = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
+        const int vp = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
+        const int fr = vp / pairs_per_frame, pr = vp - fr * pairs_per_frame;
         const int tok0 = (2 * pr + (int)rank) * a.tile_tokens;
         for (int kb = 0; kb < nkb; ++kb) {
           ok = ptx::mbar_wait(&aempty[pa.stage], pa.phase ^ 1, a.dbg, kDbgProdEmpty | (unsigned)kb);
@@ -478,11 +513,11 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
             const int tap = kb / a.kb_per_tap;
             tm = &a.tm_ring;
             c0 = (kb - tap * a.kb_per_tap) * kBK;
-            row = a.tap_row[tap] + tok0;
+            row = tcn_tap_row(a, fr, tap) + tok0;
           } else {
             tm = &a.tm_res;
             c0 = (kb - a.n_taps * a.kb_per_tap) * kBK;
-            row = a.res_row + tok0;
+            row = tcn_res_row(a, fr) + tok0;
           }
           ptx::tma_load_2d_pair_hint(sa, tm, fa, c0, row, ptx::kEvictFirst);
           ptx::tma_load_2d_pair_hint(sa + kABytes, tm, fa, c0, row + a.t_alloc, ptx::kEvictFirst);
@@ -537,7 +572,8 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
     bool ok = true;
     int it = 0;
     for (int pi = cluster_id; ok && pi < n_pairs; pi += n_clusters, ++it) {
-      const int pr = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
+      const int vp = a.reverse ? cluster_id + n_clusters * ((n_pairs - 1 - cluster_id) / n_clusters) - (pi - cluster_id) : pi;
+      const int fr = vp / pairs_per_frame, pr = vp - fr * pairs_per_frame;
       const int acc = it & 1;
       ok = ptx::mbar_wait(&tfull[acc], (it >> 1) & 1, a.dbg, kDbgEpiTmemFull | (unsigned)it);
       if (!ok) break;
@@ -546,7 +582,8 @@ __device__ __forceinline__ void tcn2_body(const TcTcnArgs &a, uint8_t *smem_raw,
       const int row = q * 32 + lane;
       const long long tok = (long long)tile * a.tile_tokens + row;
       const bool valid = tile < a.n_tiles && row < a.tile_tokens && tok < a.n_tokens;
-      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, a.epi, tok, valid);
+      const EpiArgs epi = tcn_epi(a, fr);
+      epilogue_rows<COUT, Cfg::kStacked>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::kAccCols, bias_s, epi, tok, valid);
       ptx::tc_fence_before();
       if (a.tile_cnt != nullptr) __threadfence();
       __syncwarp();
@@ -609,7 +646,29 @@ struct TcGcnArgs {
   const float *dense;
   int dense_ld, dense_vp;
   int res_in_mix;  // P = 3 only: 1 = the mix warps add the identity residual rows (epi.r_hi / r_lo), 0 = the drain warps do
+  // time-batched launch (n_frames > 1, plain graph conv only): frame f reads slot in_walk.slot(f) of the input ring and writes
+  // slot out_walk.slot(f) of the temporal ring; epi.y_* / epi.r_* then point at slot 0 of their rings
+  int n_frames = 1;
+  int slot_rows = 0;
+  RingWalk in_walk, out_walk;
+  long long in_slot_elems = 0, out_slot_elems = 0;
 };
+
+__device__ __forceinline__ int gcn_x_row(const TcGcnArgs &a, int f) { return a.n_frames == 1 ? a.x_row : a.in_walk.slot(f) * a.slot_rows; }
+__device__ __forceinline__ EpiArgs gcn_epi(const TcGcnArgs &a, int f) {
+  EpiArgs e = a.epi;
+  if (a.n_frames > 1) {
+    const long long o = (long long)a.out_walk.slot(f) * a.out_slot_elems;
+    e.y_hi += o;
+    e.y_lo += o;
+    if (e.r_hi != nullptr) {
+      const long long r = (long long)a.in_walk.slot(f) * a.in_slot_elems;
+      e.r_hi += r;
+      e.r_lo += r;
+    }
+  }
+  return e;
+}
 
 template <int P, int STAGES>
 struct TcGcnCfg {
@@ -678,8 +737,9 @@ __device__ __forceinline__ void gcn_producer(const TcGcnArgs &a, uint64_t *full,
   const int nkb = a.cin / kBK;
   PipeState ps;
   bool ok = true;
-  for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
-    const int row = a.x_row + tile * a.tile_tokens;
+  for (int vt = cta; ok && vt < a.n_tiles * a.n_frames; vt += ncta) {
+    const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
+    const int row = gcn_x_row(a, fr) + tile * a.tile_tokens;
     if (a.wait_cnt != nullptr) {
       // the input rows of this tile come from the temporal-conv role of the same launch
       const long long t0 = clock64();
@@ -726,7 +786,7 @@ __device__ __forceinline__ void gcn_mma_issuer(const TcGcnArgs &a, uint64_t *ful
   const bool mtr = TRACE && a.trace != nullptr && cta == 0;
   unsigned long long mt[2] = {0, 0};
   const long long mstart = mtr ? clock64() : 0;
-  for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+  for (int tile = cta; ok && tile < a.n_tiles * a.n_frames; tile += ncta) {
     for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
       const int acc = it & 1;
       const long long m0 = mtr ? clock64() : 0;
@@ -860,11 +920,14 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
     int it = 0;
     uint32_t xc = 0;  // exchange chunks handed over so far
     uint4 xr[4];      // next chunk's residual: 16 channels x {hi, lo} bf16
-    auto fetch_res = [&](int tile, int c0) {
+    const int n_items = a.n_tiles * a.n_frames;  // (frame, tile) work items of a time-batched launch
+    auto fetch_res = [&](int vt, int c0) {
+      const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
       const long long tok = (long long)tile * a.tile_tokens + row;
       if (has_res && row < a.tile_tokens && tok < a.n_tokens) {
-        const uint4 *ph = reinterpret_cast<const uint4 *>(a.epi.r_hi + tok * a.epi.cs_r + c0);
-        const uint4 *pl = reinterpret_cast<const uint4 *>(a.epi.r_lo + tok * a.epi.cs_r + c0);
+        const long long fo = a.n_frames > 1 ? (long long)a.in_walk.slot(fr) * a.in_slot_elems : 0;
+        const uint4 *ph = reinterpret_cast<const uint4 *>(a.epi.r_hi + fo + tok * a.epi.cs_r + c0);
+        const uint4 *pl = reinterpret_cast<const uint4 *>(a.epi.r_lo + fo + tok * a.epi.cs_r + c0);
         xr[0] = ptx::ldg_v4(ph);
         xr[1] = ptx::ldg_v4(ph + 1);
         xr[2] = ptx::ldg_v4(pl);
@@ -873,8 +936,8 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
         xr[0] = xr[1] = xr[2] = xr[3] = make_uint4(0, 0, 0, 0);
       }
     };
-    if (cta < a.n_tiles) fetch_res(cta, 0);
-    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+    if (cta < n_items) fetch_res(cta, 0);
+    for (int tile = cta; ok && tile < n_items; tile += ncta) {
       for (int pass = 0; ok && pass < n_pass; ++pass, ++it) {
         const int acc = it & 1;
         if (tr) tr_c = clock64();
@@ -902,7 +965,7 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
               nc0 = 0;
               nt = tile + ncta;
             }
-            if (nt < a.n_tiles) fetch_res(nt, nc0);
+            if (nt < n_items) fetch_res(nt, nc0);
           }
           uint32_t y0[16], y1[16], y2[16];
           ptx::tmem_ld_32x16(taddr + 0 * 64 + c * kGcnChunk, y0);
@@ -983,8 +1046,10 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
     long long tr_c = 0;
     bool ok = true;
     uint32_t xc = 0;
-    for (int tile = cta; ok && tile < a.n_tiles; tile += ncta) {
+    for (int vt = cta; ok && vt < a.n_tiles * a.n_frames; vt += ncta) {
+      const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
       const long long tok0 = (long long)tile * a.tile_tokens;
+      const EpiArgs epi = gcn_epi(a, fr);
       for (int pass = 0; ok && pass < n_pass; ++pass) {
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++xc) {
@@ -998,8 +1063,8 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
             for (int g = 0; g < 2; ++g) {
               const long long tok = tok0 + rows[g];
               if (rows[g] < a.tile_tokens && tok < a.n_tokens) {
-                rh[g] = __ldg(reinterpret_cast<const uint2 *>(a.epi.r_hi + tok * a.epi.cs_r + c0));
-                rl[g] = __ldg(reinterpret_cast<const uint2 *>(a.epi.r_lo + tok * a.epi.cs_r + c0));
+                rh[g] = __ldg(reinterpret_cast<const uint2 *>(epi.r_hi + tok * epi.cs_r + c0));
+                rl[g] = __ldg(reinterpret_cast<const uint2 *>(epi.r_lo + tok * epi.cs_r + c0));
               }
             }
           }
@@ -1037,8 +1102,8 @@ __device__ __forceinline__ void gcn_body(const TcGcnArgs &a, uint8_t *smem_raw, 
               const uint32_t h0 = pack_bf16x2(x0, x1), h1 = pack_bf16x2(x2, x3);
               const uint32_t l0 = pack_bf16x2(x0 - bf16_lo_as_float(h0), x1 - bf16_hi_as_float(h0));
               const uint32_t l1 = pack_bf16x2(x2 - bf16_lo_as_float(h1), x3 - bf16_hi_as_float(h1));
-              *reinterpret_cast<uint2 *>(a.epi.y_hi + tok * a.epi.cs_out + c0) = make_uint2(h0, h1);
-              *reinterpret_cast<uint2 *>(a.epi.y_lo + tok * a.epi.cs_out + c0) = make_uint2(l0, l1);
+              *reinterpret_cast<uint2 *>(epi.y_hi + tok * epi.cs_out + c0) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2 *>(epi.y_lo + tok * epi.cs_out + c0) = make_uint2(l0, l1);
             }
           }
           if (tr) { const long long n_ = clock64(); tr_t[1] += n_ - tr_c; tr_c = n_; }

@@ -76,6 +76,7 @@ SYMBOLS = {
     "cosk_destroy": (None, [_P]),
     "cosk_load_weights": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "cosk_set_batch": (ctypes.c_int, [_P, ctypes.c_int64]),
+    "cosk_set_batch_ex": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32]),
     "cosk_reset": (ctypes.c_int, [_P]),
     "cosk_step": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.POINTER(ctypes.c_int32), _P]),
     "cosk_steps": (ctypes.c_int, [_P, _P, ctypes.c_int32, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), _P]),

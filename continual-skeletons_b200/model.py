@@ -397,11 +397,27 @@ class _CoBase(nn.Module):
         if self._engine is not None and self._engine.n_streams is not None:
             self._engine.check(self._engine.lib.cosk_reset(self._engine.h), "cosk_reset")
 
-    def _ensure_batch(self, e, shape, n_streams):
+    def _pick_time_chunk(self, n_streams, frames):
+        """Frames per launch of forward_steps (cosk_set_batch_ex).  ``time_chunk`` > 0 is taken as given; auto (-1): the whole
+        call in one chunk when the extra ring slots fit a budget (a quarter of the free device memory, at most 8 GiB), else
+        as many frames as do; 1 when the state is first created by a single-frame call."""
+        tc = int(getattr(self, "_time_chunk", -1))
+        if tc > 0:
+            return tc
+        if frames <= 1:
+            return 1
+        per_frame = n_streams * self._S * self._V * 4 * 2 * sum(sp.cout for sp in self._specs)  # one more slot in every ring
+        free, _ = torch.cuda.mem_get_info(self._engine.device)
+        budget = min(8 << 30, free // 4)
+        return int(max(1, min(frames, budget // max(per_frame, 1), 4096)))
+
+    def _ensure_batch(self, e, shape, n_streams, frames=1):
         # models/base.py:161-164: any change of the per-step input shape resets all state
         if self._shape != shape or e.n_streams != n_streams:
-            e.check(e.lib.cosk_set_batch(e.h, int(n_streams)), "cosk_set_batch")
+            tc = self._pick_time_chunk(n_streams, frames)
+            e.check(e.lib.cosk_set_batch_ex(e.h, int(n_streams), tc), "cosk_set_batch_ex")
             e.n_streams = int(n_streams)
+            e.time_chunk = tc
             self._shape = shape
 
     @staticmethod
@@ -495,7 +511,7 @@ class _CoBase(nn.Module):
 
     def _steps(self, x, n_streams, T, shape_key, pad_end=False):
         e = self._sync(x.device)
-        self._ensure_batch(e, shape_key, n_streams)
+        self._ensure_batch(e, shape_key, n_streams, T)
         # upper bound on emissions: the last stage can emit at most once per `stride` frames; the end-of-sequence flush
         # adds at most one emission per padded frame of any stage
         max_out = T // self.stride + 1
@@ -543,6 +559,7 @@ class CoModelBase(_CoBase):
         c.add("profile_model", False)
         # this implementation
         c.add("kernel_path", "auto")
+        c.add("time_chunk", -1)  # frames per launch of forward_steps: -1 auto (see _pick_time_chunk), 1 = step by step
         return c
 
     @classmethod
@@ -572,6 +589,7 @@ class CoModelBase(_CoBase):
         self.num_classes = classes
         specs = self.block_specs(c_in)
         self._setup(specs, self.PADDING, V, S, c_in, classes, True, self.graph.A, self.hparams.kernel_path, self.ADAPTIVE)
+        self._time_chunk = int(self.hparams.time_chunk)
 
         self.data_bn = nn.BatchNorm1d(S * c_in * V)
         _init_bn(self.data_bn, 1)
@@ -727,8 +745,9 @@ class CoStack(_CoBase):
     Children are named "0", "1", ... like ``continual.Sequential`` names them
     (tests/test_cost_gcn.py:288-312 in the reference)."""
 
-    def __init__(self, blocks, padding=4, skeleton="ntu", kernel_path="auto", adaptive=False):
+    def __init__(self, blocks, padding=4, skeleton="ntu", kernel_path="auto", adaptive=False, time_chunk=-1):
         super().__init__()
+        self._time_chunk = int(time_chunk)
         g = _graph.ntu_graph() if skeleton == "ntu" else _graph.kinetics_graph()
         specs = [b if isinstance(b, BlockSpec) else BlockSpec(*b) for b in blocks]
         self._setup(specs, padding, g.num_node, 1, specs[0].cin, 0, False, g.A, kernel_path, adaptive)

@@ -109,6 +109,13 @@ int cosk_load_weights(cosk_model *m, const char *name, const float *host, size_t
 /* Stands behind clean_state_on_shape_change (models/base.py:161-164): (re)allocates all state for
  * `n_streams` concurrent streams and zeroes it. */
 int cosk_set_batch(cosk_model *m, int64_t n_streams);
+/* The same with a time chunk: cosk_steps then runs the stack module by module over chunks of up to `time_chunk` frames -- one
+ * launch per kernel and chunk, its work items (frame, tile) pairs -- the way the library's forward_steps walks a clip
+ * (models/base.py:187-190).  The temporal rings hold 8 + time_chunk slots and the input / block-output
+ * rings 4 + time_chunk (9 and 5 for time_chunk = 1, which is cosk_set_batch), so state grows with the chunk.  cosk_step is
+ * unaffected.  Stacks with a kernel outside the tensor-core CoST-GCN path (SIMT blocks, adaptive / attention graph convs)
+ * accept the call and step frame by frame. */
+int cosk_set_batch_ex(cosk_model *m, int64_t n_streams, int32_t time_chunk);
 /* Stands behind clean_state() (models/base.py:150,175): zero rings, delay lines, pool window and
  * every step counter. */
 int cosk_reset(cosk_model *m);

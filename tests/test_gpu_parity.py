@@ -266,6 +266,7 @@ def test_merged_launch_matches_separate_kernels(monkeypatch):
         monkeypatch.setenv("COSK_MERGE", merge)
         monkeypatch.setenv("COSK_MERGE_MIN_TILES", "8")
         arch, sd, m = _load_model(cs.CoStGcn, weights.cost_gcn_arch, True)
+        m._time_chunk = 1  # frame by frame: the merged launch is a per-step path
         launches0 = m.launch_count()
         outs[merge] = m.forward_steps(x).clone()
         assert m.device_error() == 0, hex(m.device_error())

@@ -166,3 +166,97 @@ def test_sharded_logits_bit_identical_to_single_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_EQUALS_SINGLE ok" in r.stdout, r.stdout[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# time-batched forward_steps: module by module over chunks of frames
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["cost_gcn", "cost_gcn_mod"])
+def test_time_batched_forward_steps_bit_identical_and_few_launches(tag, monkeypatch):
+    """forward_steps over a 300-frame clip with the stack walked module by module -- one launch per kernel and chunk, work
+    items (frame, tile) -- gives bit for bit what stepping frame by frame gives (same kernels, same per-tile arithmetic),
+    for the whole clip in one chunk, for a chunk size that makes the rings wrap inside the clip, and when stepping
+    continues frame by frame afterwards; the whole clip takes at most 40 launches (models/base.py:187-190).
+    The time-batched walk runs every block as graph conv + temporal conv launches (a launch covering many frames cannot
+    feed frame n's temporal conv from the same launch's graph conv of frame n-1), so the bit-for-bit reference is the
+    frame-by-frame path with the one-kernel block step switched off; against the default path the logits agree to rounding."""
+    monkeypatch.setenv("COSK_FUSE_BLOCK", "0")
+    cls, arch_fn, dataset, V, _ = MODELS[tag]
+    arch = arch_fn()
+    sd = weights.make_state_dict(arch, seed=8, randomize=True)
+    x = weights.make_input((7, 3, 304, V, 2), seed=61).to(DEV)  # 14 skeletons: 3 tiles, the last one ragged
+
+    def build(tc):
+        m = cls({"dataset_name": dataset, "time_chunk": tc})
+        m.load_state_dict(m.map_state_dict(sd), strict=True)
+        return m
+
+    ref = build(1)
+    want = ref.forward_steps(x)
+    per_frame_launches = ref.launch_count()
+    assert ref.device_error() == 0 and want is not None and want.dim() == 3
+    whole = build(-1)
+    got = whole.forward_steps(x)
+    assert whole.device_error() == 0
+    assert whole._engine.time_chunk == 304
+    assert whole.launch_count() <= 40, whole.launch_count()
+    assert per_frame_launches > 50 * whole.launch_count()
+    assert torch.equal(got, want)
+    chunked = build(37)
+    a = chunked.forward_steps(x[:, :, :250].contiguous())  # 6 full chunks + 28 frames
+    outs = [] if a is None else ([a] if a.dim() == 2 else [a[:, :, j] for j in range(a.shape[2])])
+    for t in range(250, 304):  # ... then frame by frame on the same state
+        o = chunked.forward_step(x[:, :, t].contiguous())
+        if o is not None:
+            outs.append(o)
+    assert chunked.device_error() == 0
+    assert len(outs) == want.shape[2]
+    for j, o in enumerate(outs):
+        assert torch.equal(o, want[:, :, j]), j
+    # and the end-of-clip flush on top of a batched clip
+    ref.clean_state()
+    full_ref = ref.forward_steps(x, pad_end=True)
+    full = build(64).forward_steps(x, pad_end=True)
+    assert torch.equal(full, full_ref)
+    # the default frame-by-frame path (64-channel blocks as one kernel per step): same logits to rounding
+    monkeypatch.delenv("COSK_FUSE_BLOCK")
+    fused = build(1)
+    assert "block" in fused_knobs(fused, x)
+    got_f = fused.forward_steps(x)
+    mag = float(want.abs().max())
+    assert float((got_f - want).abs().max()) <= 2e-4 * max(1.0, mag), (float((got_f - want).abs().max()), mag)
+    assert torch.equal(got_f.argmax(1), want.argmax(1))
+
+
+def fused_knobs(model, x):
+    """Names of the per-block kernel entries after the engine exists (one throw-away step creates it)."""
+    model.forward_step(x[:, :, 0].contiguous())
+    model.clean_state()
+    return {k for blk in model.knobs()["blocks"] for k in blk}
+
+
+def test_time_batched_strided_stack_kinetics(monkeypatch):
+    """Headless three-block stack with every residual kind and a stride-2 block on the 18-joint skeleton: chunked in time
+    (ring wrap, firing phase crossing chunk borders) == frame by frame, bit for bit (one-kernel block step off, see above),
+    and == the oracle's clip math."""
+    monkeypatch.setenv("COSK_FUSE_BLOCK", "0")
+    blocks = [weights.BlockSpec(64, 64, 1, False), weights.BlockSpec(64, 64, 1, True), weights.BlockSpec(64, 128, 2, True)]
+    arch = weights.ArchSpec(blocks, padding=4, skeleton="kinetics", head=False, block_names=["0.", "1.", "2."])
+    sd = weights.make_state_dict(arch, seed=31, randomize=True)
+    x = weights.make_input((23, 64, 45, 18), seed=32)
+    mapped = {}
+    for k, v in sd.items():
+        i, rest = k.split(".", 1)
+        kind = blocks[int(i)].res_kind
+        mapped[f"{i}.{rest}" if kind == 0 else (f"{i}.0.0.{rest}" if rest.startswith("residual") else f"{i}.0.1.{rest}")] = v
+    outs = {}
+    for tc in (1, 7, 45):
+        st = cs.CoStack([cs.BlockSpec(b.cin, b.cout, b.stride, b.residual) for b in blocks], padding=4, skeleton="kinetics", time_chunk=tc)
+        st.load_state_dict(mapped, strict=True)
+        outs[tc] = st.forward_steps(x.to(DEV))
+        assert st.device_error() == 0
+    assert torch.equal(outs[7], outs[1]) and torch.equal(outs[45], outs[1])
+    with torch.no_grad():
+        target = regular.stack_features(x, sd, arch)
+    n = outs[1].shape[2]
+    assert _rel_err(outs[1].cpu(), target[:, :, :n]) < 2e-4
