@@ -73,13 +73,8 @@ struct TcBlockArgs {
                                  // [40..46] MMA {wait G acc, wait mix slot, wait weights, wait T acc, wait history, wait tap, total},
                                  // [48..51] epilogue {wait G, G work, wait T, T work}, [52..55] producers {history wait, weights wait, x wait}
   unsigned int *dbg;
-  // time-batched launch (n_frames > 1): frame f takes x_n from x_walk.slot(f) and x_{n-4} from res_walk.slot(f) of the input
-  // ring, history tap k from (tap_walk.slot(f) + k) % tap_walk.slots of the own ring, writes g_n to g_walk.slot(f) and the
-  // block output to out_walk.slot(f); g_hi / g_lo / tepi.y_* then point at slot 0 of their rings
-  int n_frames = 1;
-  int slot_rows = 0;
-  RingWalk x_walk, res_walk, tap_walk, g_walk, out_walk;
-  long long g_slot_elems = 0, out_slot_elems = 0;
+  // (No time-batched form: frame n's temporal conv reads the graph-conv outputs of frames n-8 .. n-1, which a launch covering
+  // several frames would be producing concurrently.  cosk_steps with a time chunk runs these blocks as two launches.)
 };
 
 struct TcBlockCfg {
@@ -171,7 +166,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
   pdl_wait();  // prologue above touched only static data; activations of the previous kernel from here on
   const bool with_tcn = a.with_tcn != 0;
   const int P = a.n_parts;
-  const int n_items = a.n_tiles * a.n_frames;  // (frame, tile) work items
+  const int n_items = a.n_tiles;
   const bool tr0 = a.trace != nullptr && cta == 0;
 
   if (warp == 0) {
@@ -180,8 +175,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
       PipeState ph;
       bool ok = true;
       unsigned long long tw = 0;
-      for (int vt = cta; ok && vt < n_items; vt += ncta) {
-        const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
+      for (int tile = cta; ok && tile < n_items; tile += ncta) {
         const int tok0 = tile * a.tile_tokens;
         for (int k = 0; k < kTaps; ++k) {
           const long long w0 = tr0 ? clock64() : 0;
@@ -190,10 +184,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
           if (tr0) tw += clock64() - w0;
           const uint32_t sa = smem_base + Cfg::kHOff + ph.stage * 2 * kABytes;
           const CUtensorMap *tm = k < kTaps - 1 ? &a.tm_ring : &a.tm_x;
-          int row;
-          if (a.n_frames == 1) row = k < kTaps - 1 ? a.tap_row[k] : a.res_row;
-          else row = (k < kTaps - 1 ? (a.tap_walk.slot(fr) + k) % a.tap_walk.slots : a.res_walk.slot(fr)) * a.slot_rows;
-          row += tok0;
+          const int row = (k < kTaps - 1 ? a.tap_row[k] : a.res_row) + tok0;
           ptx::mbar_arrive_expect_tx(&hfull[ph.stage], 2 * kABytes);
           ptx::tma_load_2d_hint(sa, tm, &hfull[ph.stage], 0, row, ptx::kEvictFirst);
           ptx::tma_load_2d_hint(sa + kABytes, tm, &hfull[ph.stage], 0, row + a.t_alloc, ptx::kEvictFirst);
@@ -208,13 +199,12 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
       bool ok = true;
       int it = 0;
       unsigned long long tw = 0;
-      for (int vt = cta; ok && vt < n_items; vt += ncta, ++it) {
-        const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
+      for (int tile = cta; ok && tile < n_items; tile += ncta, ++it) {
         const long long w0 = tr0 ? clock64() : 0;
         ok = ptx::mbar_wait(xempty, (uint32_t)((it & 1) ^ 1), a.dbg, kDbgProdEmpty | 0x400000u | (unsigned)it);
         if (!ok) break;
         if (tr0) tw += clock64() - w0;
-        const int row = (a.n_frames == 1 ? a.x_row : a.x_walk.slot(fr) * a.slot_rows) + tile * a.tile_tokens;
+        const int row = a.x_row + tile * a.tile_tokens;
         ptx::mbar_arrive_expect_tx(xfull, 2 * kABytes);
         // x_n is read again four steps from now (as the delayed residual) but not before: no reason to keep it in L2
         ptx::tma_load_2d_hint(smem_base + Cfg::kXOff, &a.tm_x, xfull, 0, row, ptx::kEvictFirst);
@@ -360,18 +350,10 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
         w0 = n_;
       }
     };
-    for (int vt = cta; ok && vt < n_items; vt += ncta, ++it) {
-      const int fr = vt / a.n_tiles, tile = vt - fr * a.n_tiles;
+    for (int tile = cta; ok && tile < n_items; tile += ncta, ++it) {
       const uint32_t par = (uint32_t)(it & 1);
       const long long tok = (long long)tile * a.tile_tokens + row;
       const bool valid = row < a.tile_tokens && tok < a.n_tokens;
-      const long long g_off = a.n_frames == 1 ? 0 : (long long)a.g_walk.slot(fr) * a.g_slot_elems;
-      EpiArgs tepi = a.tepi;
-      if (a.n_frames > 1) {
-        const long long o = (long long)a.out_walk.slot(fr) * a.out_slot_elems;
-        tepi.y_hi += o;
-        tepi.y_lo += o;
-      }
       if (tr) w0 = clock64();
       ok = ptx::mbar_wait(gfull, par, a.dbg, kDbgBlkGFull | (unsigned)it);
       if (!ok) break;
@@ -398,8 +380,8 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
           ol[j] = pack_bf16x2(x0 - bf16_lo_as_float(h), x1 - bf16_hi_as_float(h));
         }
         if (valid) {
-          uint4 *qh = reinterpret_cast<uint4 *>(a.g_hi + g_off + tok * a.cs_g + c0);
-          uint4 *ql = reinterpret_cast<uint4 *>(a.g_lo + g_off + tok * a.cs_g + c0);
+          uint4 *qh = reinterpret_cast<uint4 *>(a.g_hi + tok * a.cs_g + c0);
+          uint4 *ql = reinterpret_cast<uint4 *>(a.g_lo + tok * a.cs_g + c0);
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             ptx::stg_v4(qh + w, make_uint4(oh[4 * w], oh[4 * w + 1], oh[4 * w + 2], oh[4 * w + 3]));
@@ -431,7 +413,7 @@ __global__ void __launch_bounds__(512, 1) k_tc_block64(const __grid_constant__ T
       if (!ok) break;
       lap(2);
       ptx::tc_fence_after();
-      epilogue_rows<Cfg::kC, true>(lane_base + Cfg::kTAcc, tbias_s, tepi, tok, valid);
+      epilogue_rows<Cfg::kC, true>(lane_base + Cfg::kTAcc, tbias_s, a.tepi, tok, valid);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty);

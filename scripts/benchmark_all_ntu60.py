@@ -30,8 +30,9 @@ DEFAULT_BATCH, DEFAULT_RUNS = 256, 100  # the reference's continual GPU setting 
 
 
 def profile_model(name, batch_size, num_runs, dataset_name, device):
+    # time_chunk = 1: the protocol is per-step inference; the rings stay at their per-step size (9 / 5 slots)
     model = MODELS[name]({"dataset_name": dataset_name, "forward_mode": "frame", "profile_model": True,
-                          "batch_size": batch_size})
+                          "batch_size": batch_size, "time_chunk": 1})
     c, t, v, s = model.input_shape  # t == model.stride in profiling mode
     sample = torch.rand((batch_size, c, t, v, s), device=device)
     model.warm_up(None, sample)
