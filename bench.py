@@ -238,6 +238,8 @@ def kernel_label(path, kname, cin, cout, kblock, workload, knobs):
         return f"k_gcn_small (layer {kblock + 1})", r"k_gcn_small"
     if "gcnp" in knobs.get("graph_conv", {}).get(str(cout), ""):
         return f"k_tc_gcnp<{cout}> (layer {kblock + 1}; pre-mix, A operand in TMEM)", rf"k_tc_gcnp<{cout},"
+    if "gcnt" in knobs.get("graph_conv", {}).get(str(cout), "") and cin <= 128:
+        return f"k_tc_gcnt C={cout} (layer {kblock + 1}; channel-major GEMM, adjacency mix in registers)", r"k_tc_gcnt<"
     return f"k_tc_gcn C={cout} (layer {kblock + 1}; GEMM-then-mix)", r"k_tc_gcn<"
 
 

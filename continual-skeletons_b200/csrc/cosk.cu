@@ -17,6 +17,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_gcnp.cuh"
+#include "tc_gcnt.cuh"
 #include "tc_block.cuh"
 
 using namespace cosk;
@@ -91,6 +92,12 @@ struct BlockW {
   int gcnp_parts = 3;
   __nv_bfloat16 *d_gcnp_w16 = nullptr;
   CUtensorMap map_gcnp_w;
+  // channel-major graph conv (k_tc_gcnt): weights [2 planes][chunk of 128 channels][part][128] x cin, tree coefficients
+  bool tc_gcnt = false;
+  int gcnt_parts = 4;
+  __nv_bfloat16 *d_gcnt_w16 = nullptr;
+  CUtensorMap map_gcnt_w;
+  float gcnt_coef[3][32];
   bool tc_attn = false;  // adaptive graph conv: attention half on the tcgen05 kernel
   bool gcn_res_in_mix = false;  // P = 3 plain graph conv: identity residual added by the mix warps (else by the drain warps)
   bool tcn_res_kblock = false;  // tensor-core temporal conv: the residual enters as extra K-blocks of the GEMM (folded
@@ -131,6 +138,9 @@ struct cosk_model {
                        // bit 2: 256 output channels); the rest stays on k_tc_gcn (COSK_GCN_PREMIX).  Off: measured slower standalone
                        // (profiles/r2a_gcnp_ab.txt) -- its CUDA-core mix only pays off hidden under the temporal conv's HBM stream
   int gcn_fold_unit = 1;  // k_tc_gcn: fold the gcn_residual branch into W_0 when every self link is exactly 1 (COSK_GCN_FOLD_UNIT=0 disables)
+  int gcn_transposed = 1;  // plain graph convs with cout in {128, 256}, cin in {64, 128} on a skeleton tree the kernel is compiled for run on
+                           // k_tc_gcnt (channels on the TMEM lanes, adjacency contraction in registers); COSK_GCN_T=0: k_tc_gcn
+  int gcnt_pack = 1;  // k_tc_gcnt: lane pairs trade tokens before the store (32-bit stores of two channels); COSK_GCNT_PACK=0: 16-bit stores
   int fuse_block = 1;  // 64 -> 64 identity-residual blocks: graph conv + temporal conv in one kernel per step (COSK_FUSE_BLOCK=0: two kernels)
   int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
   int pair_mask = 6;  // which temporal-conv widths run on CTA pairs (bit 0: 64, bit 1: 128, bit 2: 256); COSK_TCN_PAIR
@@ -440,6 +450,51 @@ int prepare(cosk_model *m) {
       if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcn_w16), s.data(), s.size()))) return rc;
       if ((rc = make_map(m, &b.map_gcn_w, b.d_gcn_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, (uint32_t)(P * 64)))) return rc;
     }
+    b.tc_gcnt = false;
+    if (b.tc_gcn && !adaptive && !attention && m->gcn_transposed && (bc.cout == 128 || bc.cout == 256) &&
+        (bc.cin == 64 || bc.cin == 128) && (V == 25 || V == 18) && b.mix_diag0) {
+      // The mixing matrix must have exactly the sparsity of the skeleton tree the kernel is compiled for: partition 1 = one
+      // entry per vertex, from its parent; partition 2 = entries from a vertex's children.
+      auto parent = [&](int w) { return V == 25 ? skel_parent<25>(w) : skel_parent<18>(w); };
+      bool tree = true;
+      memset(b.gcnt_coef, 0, sizeof b.gcnt_coef);
+      for (int v = 0; v < V; ++v)
+        for (int w = 0; w < V; ++w) {
+          const float a0 = b.mix[((size_t)0 * V + v) * V + w], a1 = b.mix[((size_t)1 * V + v) * V + w],
+                      a2 = b.mix[((size_t)2 * V + v) * V + w];
+          if (v == w) b.gcnt_coef[0][w] = a0;
+          if (a1 != 0.f) {
+            if (parent(w) == v) b.gcnt_coef[1][w] = a1;
+            else tree = false;
+          }
+          if (a2 != 0.f) {
+            if (parent(v) == w) b.gcnt_coef[2][v] = a2;
+            else tree = false;
+          }
+        }
+      if (tree) {
+        // as for k_tc_gcn: every self link exactly 1 -> gcn_residual folded into W_0, three parts; else the residual (folded
+        // 1x1 conv, or the identity matrix) is a fourth part
+        const int P = b.gcnt_parts = b.gcn_folded ? 3 : 4;
+        std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
+        for (int o = 0; o < bc.cout; ++o)
+          for (int part = 0; part < P; ++part) {
+            float *row = &re[(((size_t)(o / 128) * P + part) * 128 + (o % 128)) * bc.cin];
+            if (part < 3 || res_conv) memcpy(row, &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
+            else row[o] = 1.0f;
+            if (b.gcn_folded && part == 0) {
+              if (res_conv)
+                for (int k = 0; k < bc.cin; ++k) row[k] += b.gcn_w[(size_t)o * Kg + (size_t)3 * bc.cin + k];
+              else
+                row[o] += 1.0f;
+            }
+          }
+        std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
+        if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcnt_w16), s.data(), s.size()))) return rc;
+        if ((rc = make_map(m, &b.map_gcnt_w, b.d_gcnt_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, 128u))) return rc;
+        b.tc_gcnt = true;
+      }
+    }
     {
       // pre-mix kernel: sources per (partition >= 1, output vertex) must fit its register CSR
       int part_max = 0;
@@ -729,6 +784,12 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcnp<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnp<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<256, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_block64, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBlockCfg::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<25, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<18, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<18, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<18, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<18, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_gcnt<18, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<18, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_tcn_gcn<64, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           std::max(TcTcnCfg<64>::kSmemBytes, TcGcnCfg<4, 1>::kSmemBytes)));
   CK(cudaFuncSetAttribute(k_tc_tcn2_gcn<128, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -770,6 +831,33 @@ TcGcnArgs make_gcn_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int
   a.dense_vp = m->dense_vp;
   a.res_in_mix = b.gcn_res_in_mix ? 1 : 0;
   return a;
+}
+
+// k_tc_gcnt: `a` as for k_tc_gcn (per-frame or time-batched); work items are pairs of adjacent tiles
+int launch_tc_gcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  const BlockW &b = m->blk[i];
+  TcGcntArgs t;
+  t.g = a;
+  t.g.tm_w = b.map_gcnt_w;
+  t.g.epi.r_hi = t.g.epi.r_lo = nullptr;  // gcn_residual always rides in the GEMM here
+  memcpy(t.coef, b.gcnt_coef, sizeof t.coef);
+  t.n_parts = b.gcnt_parts;
+  t.pack = m->gcnt_pack;
+  const int items = ((m->n_tiles + 1) / 2) * a.n_frames;
+  const dim3 grid(items < m->num_sms ? items : m->num_sms), block(384);
+  const bool v25 = m->cfg.vertices == 25;
+  if (bc.cout == 128 && bc.cin == 64) {
+    if (v25) CK(launch_k(m, k_tc_gcnt<25, 1, 128>, grid, block, TcGcntCfg<25, 1>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_gcnt<18, 1, 128>, grid, block, TcGcntCfg<18, 1>::kSmemBytes, s, t));
+  } else if (bc.cout == 128) {
+    if (v25) CK(launch_k(m, k_tc_gcnt<25, 2, 128>, grid, block, TcGcntCfg<25, 2>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_gcnt<18, 2, 128>, grid, block, TcGcntCfg<18, 2>::kSmemBytes, s, t));
+  } else {
+    if (v25) CK(launch_k(m, k_tc_gcnt<25, 2, 256>, grid, block, TcGcntCfg<25, 2>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_gcnt<18, 2, 256>, grid, block, TcGcntCfg<18, 2>::kSmemBytes, s, t));
+  }
+  return COSK_OK;
 }
 
 TcGcnpArgs make_gcnp_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot) {
@@ -846,7 +934,7 @@ bool can_merge(const cosk_model *m, int i) {
   if (!m->merge || i + 1 >= m->cfg.n_blocks || m->d_trace || m->cfg.blocks[i + 1].gconv != COSK_GCONV_PLAIN) return false;
   const BlockW &b = m->blk[i], &nb = m->blk[i + 1];
   const int c = m->cfg.blocks[i].cout;
-  if (!b.tc_tcn || !nb.tc_gcn || nb.tc_gcnp || nb.fuse || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
+  if (!b.tc_tcn || !nb.tc_gcn || nb.tc_gcnp || nb.tc_gcnt || nb.fuse || nb.gcn_parts != 4 || b.d_tile_cnt == nullptr) return false;
   if (m->n_tiles < m->merge_min_tiles) return false;
   if (c == 64) return m->gcn_single_stage && !(m->pair_mask & 1);
   if (c == 128) return (m->pair_mask & 2) != 0;
@@ -1154,6 +1242,8 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     if (b.gcn_parts == 4) rc = v25 ? launch_tc_agcn<4, 1, 25>(m, a, s) : launch_tc_agcn<4, 1, 18>(m, a, s);
     else rc = v25 ? launch_tc_agcn<3, 2, 25>(m, a, s) : launch_tc_agcn<3, 2, 18>(m, a, s);
     if (rc) return rc;
+  } else if (b.tc_gcnt) {
+    if ((rc = launch_tc_gcnt(m, i, make_gcn_args(m, i, in, in_slot, ring_slot), s))) return rc;
   } else if (b.tc_gcnp) {
     TcGcnpArgs a = make_gcnp_args(m, i, in, in_slot, ring_slot);
     if (bc.cout == 64) rc = b.gcnp_stacked ? launch_tc_gcnp<64, true>(m, a, s) : launch_tc_gcnp<64, false>(m, a, s);
@@ -1501,7 +1591,9 @@ int steps_chunk(cosk_model *m, const float *x, long long nc_stride, long long x_
         const bool one_kb = bc.cin == kBK && m->gcn_single_stage;
         const int items = m->n_tiles * F;
         const int grid = items < m->num_sms ? items : m->num_sms;
-        if (b.gcn_parts == 4) {
+        if (b.tc_gcnt) {
+          if ((rc = launch_tc_gcnt(m, i, a, s))) return rc;
+        } else if (b.gcn_parts == 4) {
           if (one_kb) CK(launch_k(m, k_tc_gcn<4, 1, false>, dim3(grid), dim3(512), TcGcnCfg<4, 1>::kSmemBytes, s, a));
           else CK(launch_k(m, k_tc_gcn<4, 2, false>, dim3(grid), dim3(512), TcGcnCfg<4, 2>::kSmemBytes, s, a));
         } else {
@@ -1694,6 +1786,8 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_PDL")) m->pdl = atoi(e);
   if (const char *e = getenv("COSK_GCN_PREMIX")) m->gcn_premix = atoi(e);
   if (const char *e = getenv("COSK_FUSE_BLOCK")) m->fuse_block = atoi(e);
+  if (const char *e = getenv("COSK_GCN_T")) m->gcn_transposed = atoi(e);
+  if (const char *e = getenv("COSK_GCNT_PACK")) m->gcnt_pack = atoi(e);
   if (const char *e = getenv("COSK_GCN_FOLD_UNIT")) m->gcn_fold_unit = atoi(e);
   if (const char *e = getenv("COSK_GCNP_STACKED")) m->gcnp_stacked = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
@@ -1765,6 +1859,7 @@ void cosk_destroy(cosk_model *m) {
     dfree(b.d_adj);
     dfree(b.d_gcn_w16);
     dfree(b.d_gcnp_w16);
+    dfree(b.d_gcnt_w16);
     dfree(b.d_tcn_w16);
     dfree(b.d_att_w16);
     dfree(b.d_sa_scale);
@@ -2054,10 +2149,10 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
   char t[1024];
   snprintf(t, sizeof t,
            "\"version\": \"%s\", \"path\": \"%s\", \"pdl\": %d, \"tcn_pair_mask\": %d, \"tcn_reverse\": %d, \"tcn_identity_mma\": %d, "
-           "\"fuse_block\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
+           "\"fuse_block\": %d, \"gcn_transposed\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
            "\"sa_fused\": %d, \"attn_tc\": %d, \"agcn_tc\": %d, \"trace\": %d, ",
            cosk_version(), m->cfg.path == COSK_PATH_AUTO ? "auto" : "simt", m->pdl, m->pair_mask, m->tcn_reverse, m->tcn_identity_mma,
-           m->fuse_block, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
+           m->fuse_block, m->gcn_transposed, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
            m->d_trace ? 1 : 0);
   o += t;
   o += "\"blocks\": [";
@@ -2068,7 +2163,10 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
     std::string g, tc;
     if (bc.gconv == COSK_GCONV_ATTENTION) g = b.tc_sa_fused ? "k_tc_sa" : (b.tc_sa_qkv ? "k_tc_tcn(qkv)+k_sa_attn" : "k_sa_qkv+k_sa_attn");
     else if (bc.gconv == COSK_GCONV_ADAPTIVE) g = b.tc_gcn ? (b.tc_attn ? "k_tc_attn+k_tc_agcn" : "k_agcn_attn+k_tc_agcn") : "k_agcn_attn+k_gcn_simt";
-    else if (b.tc_gcnp) {
+    else if (b.tc_gcnt) {
+      snprintf(t, sizeof t, "k_tc_gcnt<%d> channel-major, mix in registers", b.gcnt_parts);
+      g = t;
+    } else if (b.tc_gcnp) {
       snprintf(t, sizeof t, "k_tc_gcnp<%d,%s> P=%d", bc.cout, b.gcnp_stacked ? "stacked" : "3-product", b.gcnp_parts);
       g = t;
     } else if (b.tc_gcn) {
@@ -2093,7 +2191,7 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
   for (int w : {64, 128, 256})
     for (int i = 0; i < m->cfg.n_blocks; ++i)
       if (m->cfg.blocks[i].cout == w && m->cfg.blocks[i].cin >= 64 && m->cfg.blocks[i].gconv == COSK_GCONV_PLAIN) {
-        snprintf(t, sizeof t, "%s\"%d\": \"%s\"", firstw ? "" : ", ", w, m->blk[i].tc_gcnp ? "gcnp" : m->blk[i].tc_gcn ? "gcn" : "simt");
+        snprintf(t, sizeof t, "%s\"%d\": \"%s\"", firstw ? "" : ", ", w, m->blk[i].tc_gcnt ? "gcnt" : m->blk[i].tc_gcnp ? "gcnp" : m->blk[i].tc_gcn ? "gcn" : "simt");
         o += t;
         firstw = false;
         break;

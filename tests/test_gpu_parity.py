@@ -197,6 +197,51 @@ def test_long_run_pool_window_exact():
     assert torch.equal(outs[-1], outs[-2]) and torch.equal(outs[-1], outs[-40])
 
 
+def _load_stack(stack, sd, blocks):
+    mapped = {}
+    for k, v in sd.items():
+        i, rest = k.split(".", 1)
+        spec = blocks[int(i)]
+        if spec.res_kind == 0:
+            mapped[f"{i}.{rest}"] = v
+        elif rest.startswith("residual"):
+            mapped[f"{i}.0.0.{rest}"] = v
+        else:
+            mapped[f"{i}.0.1.{rest}"] = v
+    stack.load_state_dict(mapped, strict=True)
+
+
+@pytest.mark.parametrize("rnd", [False, True])
+@pytest.mark.parametrize("skeleton,V,B", [("ntu", 25, 23), ("ntu", 25, 1495), ("kinetics", 18, 23)])
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 128), (128, 256)])
+def test_channel_major_graph_conv(monkeypatch, cin, cout, skeleton, V, B, rnd):
+    """k_tc_gcnt (channels on the TMEM lanes, adjacency contraction in registers along the compiled-in skeleton tree):
+    selected for the 128/256-channel plain graph convs of both skeletons, equal to the oracle's clip math with distinct
+    streams, a phantom second tile in the last pair (odd tile counts), more tile pairs than SMs (B = 1495 -> 299 tiles), unit
+    self links (three parts, gcn_residual folded into W_0) and trained ones (four parts) -- and to the token-major kernel."""
+    blocks = [weights.BlockSpec(cin, cout, 1, True)]
+    arch = ArchSpec(blocks, padding=4, skeleton=skeleton, head=False, block_names=["0."])
+    sd = weights.make_state_dict(arch, seed=77 + cin + cout, randomize=rnd)
+    T = 12
+    x = weights.make_input((B, cin, T, V), seed=78)
+    with torch.no_grad():
+        target = regular.stack_features(x, sd, arch)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("COSK_GCN_T", flag)
+        stack = cs.CoStack([cs.BlockSpec(cin, cout, 1, True)], padding=4, skeleton=skeleton)
+        _load_stack(stack, sd, blocks)
+        out = stack.forward_steps(x.to(DEV))
+        assert stack.device_error() == 0
+        kernel = stack.knobs()["blocks"][0]["gcn"]
+        assert kernel.startswith("k_tc_gcnt<%d>" % (4 if rnd else 3)) if flag == "1" else kernel.startswith("k_tc_gcn<")
+        outs[flag] = out.cpu()
+    n = outs["1"].shape[2]
+    assert n == target.shape[2] - arch.stack_padding // arch.stack_stride
+    assert _rel_err(outs["1"], target[:, :, :n]) < BLOCK_RTOL
+    assert _rel_err(outs["1"], outs["0"]) < 2e-5  # same products, different fp32 summation order of the mix
+
+
 @pytest.mark.parametrize("path", ["simt", "auto"])
 def test_kinetics_skeleton_stack(path):
     """V = 18 (OpenPose) graph, 7 skeletons = 126 token rows per tile, a strided 3-block stack with every
@@ -265,6 +310,7 @@ def test_merged_launch_matches_separate_kernels(monkeypatch):
     for merge in ("0", "1"):
         monkeypatch.setenv("COSK_MERGE", merge)
         monkeypatch.setenv("COSK_MERGE_MIN_TILES", "8")
+        monkeypatch.setenv("COSK_GCN_T", "0")  # the merged launch pairs the temporal conv with the token-major graph conv
         arch, sd, m = _load_model(cs.CoStGcn, weights.cost_gcn_arch, True)
         m._time_chunk = 1  # frame by frame: the merged launch is a per-step path
         launches0 = m.launch_count()
