@@ -817,12 +817,23 @@ __global__ void __launch_bounds__(256 * kHeadStreams) k_head(HeadArgs a) {
         for (int s = half; s < a.S; s += 2) {
           float p0 = 0.f, p1 = 0.f;
           const long long base = (tok0 + (long long)s * a.V) * a.cs + 2 * cp;
-#pragma unroll 5
-          for (int v = 0; v < a.V; ++v) {
-            const uint32_t h = *reinterpret_cast<const uint32_t *>(y_hi + base + (long long)v * a.cs);
-            const uint32_t l = *reinterpret_cast<const uint32_t *>(y_lo + base + (long long)v * a.cs);
-            p0 += bf16_lo_as_float(h) + bf16_lo_as_float(l);
-            p1 += bf16_hi_as_float(h) + bf16_hi_as_float(l);
+          // rows in batches of 13 (26 loads in flight per thread: the kernel is bound by HBM latency x bytes in flight);
+          // the sums run in vertex order whatever the batch size
+          constexpr int kVB = 13;
+          for (int v0 = 0; v0 < a.V; v0 += kVB) {
+            uint32_t h[kVB], l[kVB];
+#pragma unroll
+            for (int j = 0; j < kVB; ++j) {
+              const bool on = v0 + j < a.V;
+              h[j] = on ? __ldg(reinterpret_cast<const unsigned int *>(y_hi + base + (long long)(v0 + j) * a.cs)) : 0u;
+              l[j] = on ? __ldg(reinterpret_cast<const unsigned int *>(y_lo + base + (long long)(v0 + j) * a.cs)) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kVB; ++j)
+              if (v0 + j < a.V) {
+                p0 += bf16_lo_as_float(h[j]) + bf16_lo_as_float(l[j]);
+                p1 += bf16_hi_as_float(h[j]) + bf16_hi_as_float(l[j]);
+              }
           }
           t0 += p0 / (float)a.V;
           t1 += p1 / (float)a.V;
