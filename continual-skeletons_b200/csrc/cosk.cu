@@ -18,6 +18,7 @@
 #include "tc_kernels.cuh"
 #include "tc_gcnp.cuh"
 #include "tc_gcnt.cuh"
+#include "tc_agcnt.cuh"
 #include "tc_block.cuh"
 
 using namespace cosk;
@@ -94,6 +95,7 @@ struct BlockW {
   CUtensorMap map_gcnp_w;
   // channel-major graph conv (k_tc_gcnt): weights [2 planes][chunk of 128 channels][part][128] x cin, tree coefficients
   bool tc_gcnt = false;
+  bool tc_agcnt = false;  // adaptive graph conv: dense mix on the channel-major kernel k_tc_agcnt (same weight layout, always 4 parts)
   int gcnt_parts = 4;
   __nv_bfloat16 *d_gcnt_w16 = nullptr;
   CUtensorMap map_gcnt_w;
@@ -140,6 +142,9 @@ struct cosk_model {
   int gcn_fold_unit = 1;  // k_tc_gcn: fold the gcn_residual branch into W_0 when every self link is exactly 1 (COSK_GCN_FOLD_UNIT=0 disables)
   int gcn_transposed = 1;  // plain graph convs with cout in {128, 256}, cin in {64, 128} on a skeleton tree the kernel is compiled for run on
                            // k_tc_gcnt (channels on the TMEM lanes, adjacency contraction in registers); COSK_GCN_T=0: k_tc_gcn
+  int agcn_transposed = 0;  // adaptive graph convs with cout in {128, 256}, cin in {64, 128}: dense mix on k_tc_agcnt.  OFF: the kernel was
+                            // written after the round's GPU budget was spent -- it compiles (no spills) but has never run on hardware.
+                            // COSK_AGCN_T=1 enables it (tests/test_gpu_parity.py::test_channel_major_adaptive_graph_conv, COSK_TEST_UNVERIFIED=1)
   int gcnt_pack = 1;  // k_tc_gcnt: lane pairs trade tokens before the store (32-bit stores of two channels); COSK_GCNT_PACK=0: 16-bit stores
   int fuse_block = 1;  // 64 -> 64 identity-residual blocks: graph conv + temporal conv in one kernel per step (COSK_FUSE_BLOCK=0: two kernels)
   int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
@@ -495,6 +500,24 @@ int prepare(cosk_model *m) {
         b.tc_gcnt = true;
       }
     }
+    b.tc_agcnt = false;
+    if (b.tc_gcn && adaptive && m->agcn_transposed && (bc.cout == 128 || bc.cout == 256) && (bc.cin == 64 || bc.cin == 128) &&
+        (V == 25 || V == 18)) {
+      // channel-major layout, always four parts: W_0, W_1, W_2, gcn_residual (folded 1x1 conv, or the identity matrix)
+      const int P = 4;
+      std::vector<float> re((size_t)P * bc.cout * bc.cin, 0.f);
+      for (int o = 0; o < bc.cout; ++o)
+        for (int part = 0; part < P; ++part) {
+          float *row = &re[(((size_t)(o / 128) * P + part) * 128 + (o % 128)) * bc.cin];
+          if (part < 3 || res_conv) memcpy(row, &b.gcn_w[(size_t)o * Kg + (size_t)part * bc.cin], sizeof(float) * bc.cin);
+          else row[o] = 1.0f;
+        }
+      std::vector<uint16_t> s = split_rows(re, P * bc.cout, bc.cin);
+      if ((rc = upload(m, reinterpret_cast<uint16_t *&>(b.d_gcnt_w16), s.data(), s.size()))) return rc;
+      if ((rc = make_map(m, &b.map_gcnt_w, b.d_gcnt_w16, (uint64_t)bc.cin, (uint64_t)2 * P * bc.cout, 128u))) return rc;
+      b.gcnt_parts = P;
+      b.tc_agcnt = true;
+    }
     {
       // pre-mix kernel: sources per (partition >= 1, output vertex) must fit its register CSR
       int part_max = 0;
@@ -784,6 +807,12 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcnp<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnp<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<256, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_block64, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBlockCfg::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<25, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<25, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<25, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<18, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 1>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<18, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 2>::kSmemBytes));
+  CK(cudaFuncSetAttribute(k_tc_agcnt<18, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
@@ -856,6 +885,33 @@ int launch_tc_gcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
   } else {
     if (v25) CK(launch_k(m, k_tc_gcnt<25, 2, 256>, grid, block, TcGcntCfg<25, 2>::kSmemBytes, s, t));
     else CK(launch_k(m, k_tc_gcnt<18, 2, 256>, grid, block, TcGcntCfg<18, 2>::kSmemBytes, s, t));
+  }
+  return COSK_OK;
+}
+
+// k_tc_agcnt: dense mix of the adaptive graph conv, work items are single tiles
+int launch_tc_agcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
+  const cosk_block_cfg &bc = m->cfg.blocks[i];
+  const BlockW &b = m->blk[i];
+  TcGcntArgs t;
+  t.g = a;
+  t.g.tm_w = b.map_gcnt_w;
+  t.g.epi.r_hi = t.g.epi.r_lo = nullptr;  // gcn_residual rides in the GEMM as the fourth part
+  memset(t.coef, 0, sizeof t.coef);
+  t.n_parts = 4;
+  t.pack = 1;
+  const int items = m->n_tiles * a.n_frames;
+  const dim3 grid(items < m->num_sms ? items : m->num_sms), block(384);
+  const bool v25 = m->cfg.vertices == 25;
+  if (bc.cout == 128 && bc.cin == 64) {
+    if (v25) CK(launch_k(m, k_tc_agcnt<25, 1, 128>, grid, block, TcAgcntCfg<25, 1>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_agcnt<18, 1, 128>, grid, block, TcAgcntCfg<18, 1>::kSmemBytes, s, t));
+  } else if (bc.cout == 128) {
+    if (v25) CK(launch_k(m, k_tc_agcnt<25, 2, 128>, grid, block, TcAgcntCfg<25, 2>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_agcnt<18, 2, 128>, grid, block, TcAgcntCfg<18, 2>::kSmemBytes, s, t));
+  } else {
+    if (v25) CK(launch_k(m, k_tc_agcnt<25, 2, 256>, grid, block, TcAgcntCfg<25, 2>::kSmemBytes, s, t));
+    else CK(launch_k(m, k_tc_agcnt<18, 2, 256>, grid, block, TcAgcntCfg<18, 2>::kSmemBytes, s, t));
   }
   return COSK_OK;
 }
@@ -1236,7 +1292,9 @@ int run_gcn(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot, 
     m->launches++;
     if ((rc = prof_mark(m, 1, i, s))) return rc;
   }
-  if (b.tc_gcn && adaptive) {
+  if (b.tc_agcnt) {
+    if ((rc = launch_tc_agcnt(m, i, make_gcn_args(m, i, in, in_slot, ring_slot), s))) return rc;
+  } else if (b.tc_gcn && adaptive) {
     TcGcnArgs a = make_gcn_args(m, i, in, in_slot, ring_slot);
     const bool v25 = m->cfg.vertices == 25;
     if (b.gcn_parts == 4) rc = v25 ? launch_tc_agcn<4, 1, 25>(m, a, s) : launch_tc_agcn<4, 1, 18>(m, a, s);
@@ -1788,6 +1846,7 @@ int cosk_create(const cosk_config *cfg, cosk_model **out) {
   if (const char *e = getenv("COSK_FUSE_BLOCK")) m->fuse_block = atoi(e);
   if (const char *e = getenv("COSK_GCN_T")) m->gcn_transposed = atoi(e);
   if (const char *e = getenv("COSK_GCNT_PACK")) m->gcnt_pack = atoi(e);
+  if (const char *e = getenv("COSK_AGCN_T")) m->agcn_transposed = atoi(e);
   if (const char *e = getenv("COSK_GCN_FOLD_UNIT")) m->gcn_fold_unit = atoi(e);
   if (const char *e = getenv("COSK_GCNP_STACKED")) m->gcnp_stacked = atoi(e);
   if (const char *e = getenv("COSK_AGCN_TC")) m->agcn_tc = atoi(e);
@@ -2149,10 +2208,10 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
   char t[1024];
   snprintf(t, sizeof t,
            "\"version\": \"%s\", \"path\": \"%s\", \"pdl\": %d, \"tcn_pair_mask\": %d, \"tcn_reverse\": %d, \"tcn_identity_mma\": %d, "
-           "\"fuse_block\": %d, \"gcn_transposed\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
+           "\"fuse_block\": %d, \"gcn_transposed\": %d, \"agcn_transposed\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
            "\"sa_fused\": %d, \"attn_tc\": %d, \"agcn_tc\": %d, \"trace\": %d, ",
            cosk_version(), m->cfg.path == COSK_PATH_AUTO ? "auto" : "simt", m->pdl, m->pair_mask, m->tcn_reverse, m->tcn_identity_mma,
-           m->fuse_block, m->gcn_transposed, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
+           m->fuse_block, m->gcn_transposed, m->agcn_transposed, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
            m->d_trace ? 1 : 0);
   o += t;
   o += "\"blocks\": [";
@@ -2162,6 +2221,7 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
     const BlockW &b = m->blk[i];
     std::string g, tc;
     if (bc.gconv == COSK_GCONV_ATTENTION) g = b.tc_sa_fused ? "k_tc_sa" : (b.tc_sa_qkv ? "k_tc_tcn(qkv)+k_sa_attn" : "k_sa_qkv+k_sa_attn");
+    else if (bc.gconv == COSK_GCONV_ADAPTIVE && b.tc_agcnt) g = b.tc_attn ? "k_tc_attn+k_tc_agcnt" : "k_agcn_attn+k_tc_agcnt";
     else if (bc.gconv == COSK_GCONV_ADAPTIVE) g = b.tc_gcn ? (b.tc_attn ? "k_tc_attn+k_tc_agcn" : "k_agcn_attn+k_tc_agcn") : "k_agcn_attn+k_gcn_simt";
     else if (b.tc_gcnt) {
       snprintf(t, sizeof t, "k_tc_gcnt<%d> channel-major, mix in registers", b.gcnt_parts);

@@ -79,8 +79,12 @@ struct TcBlockArgs {
 
 struct TcBlockCfg {
   static constexpr int kC = 64;
-  static constexpr int kHStages = 4;  // history ring
-  static constexpr int kBStages = 3;
+#ifndef COSK_BLK_HSTAGES
+#define COSK_BLK_HSTAGES 4
+#define COSK_BLK_BSTAGES 3
+#endif
+  static constexpr int kHStages = COSK_BLK_HSTAGES;  // history ring
+  static constexpr int kBStages = COSK_BLK_BSTAGES;
   static constexpr int kSlabBytes = 2 * kC * kBK * 2;  // 16 KB: [64 hi rows; 64 lo rows] x 64 K
   static constexpr int kXOff = 0;                      // x_n tile: hi plane, lo plane; later the fp32 rows of the same tile
   static constexpr int kHOff = 2 * kABytes;

@@ -49,23 +49,43 @@ def _sources():
     ]
 
 
+def _fresh(out):
+    return os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in _sources())
+
+
 def build_library(force=False, verbose=False):
-    """nvcc cross-compiles for sm_100a; no GPU needed.  Rebuilds when a source is newer."""
+    """nvcc cross-compiles for sm_100a; no GPU needed.  Rebuilds when a source is newer.
+
+    Safe under concurrency (N ranks of one job importing the package at once): the build runs under an exclusive file
+    lock, a rank that waited re-checks freshness instead of building again, the compiler writes to a per-process
+    temporary and the result is moved into place atomically -- no rank can ever dlopen a half-written library."""
+    import fcntl
+
     out = library_path()
-    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in _sources()):
+    if not force and _fresh(out):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise CoskError("nvcc not found: cannot build libcosk.so")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", out + ".tmp", os.path.join(CSRC, "cosk.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise CoskError("nvcc failed:\n" + r.stdout + r.stderr)
-    os.replace(out + ".tmp", out)
-    if verbose:
-        print(r.stderr)
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _fresh(out):  # another process built it while this one waited
+                return out
+            tmp = f"{out}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "cosk.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise CoskError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, out)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
 
 

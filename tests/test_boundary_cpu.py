@@ -305,3 +305,34 @@ def test_bench_algorithmic_cost_matches_survey_totals():
     assert abs(k["state"] - 1.01376e6) < 1 and abs(k["flops"] / 2 - 41.0e6) < 0.05e6
     blk = a["blocks"][1]  # a 64 -> 64 block: 11 frames of 25 x 64 x 4 B per skeleton, two skeletons per stream
     assert blk["gcn_bytes"] + blk["tcn_bytes"] == 2 * 70400
+
+
+@pytest.mark.parametrize("V,graph_fn", [(25, cs.graph.ntu_graph), (18, cs.graph.kinetics_graph)])
+def test_compiled_skeleton_trees_match_the_graph(V, graph_fn):
+    """k_tc_gcnt (csrc/tc_gcnt.cuh) contracts the adjacency along a skeleton tree that is fixed at compile time
+    (skel_parent<V>): partition 1 must be exactly "vertex <- its parent", partition 2 exactly "parent <- its children",
+    partition 0 the identity -- the sparsity of the reference's graph (datasets/graph.py:9-44 with the edge lists of
+    datasets/ntu_rgbd.py:3-35 and datasets/kinetics.py:24-46), which graph.py reproduces bit for bit."""
+    src = open(os.path.join(ROOT, "continual-skeletons_b200", "csrc", "tc_gcnt.cuh")).read()
+    m = re.search(r"skel_parent<%d>\(int w\) \{[^\n]*\n\s*constexpr int p\[%d\] = \{([^}]*)\};" % (V, V), src)
+    assert m, "parent table not found"
+    parent = [int(t) for t in m.group(1).split(",")]
+    assert len(parent) == V and parent.count(-1) == 1
+    A = graph_fn().A
+    assert A.shape == (3, V, V)
+    want1 = np.zeros((V, V), dtype=bool)  # [v, w]: z[w] += A_1[v, w] * y[v], v = parent(w)
+    want2 = np.zeros((V, V), dtype=bool)  # [v, w]: v = child, w = parent(v)
+    for w, p in enumerate(parent):
+        if p >= 0:
+            want1[p, w] = True
+            want2[w, p] = True
+    assert np.array_equal(A[0] != 0, np.eye(V, dtype=bool))
+    assert np.array_equal(A[1] != 0, want1)
+    assert np.array_equal(A[2] != 0, want2)
+    # every vertex reaches the root: the table is a tree, not a forest with a cycle
+    root = parent.index(-1)
+    for w in range(V):
+        seen, v = 0, w
+        while v != root:
+            v, seen = parent[v], seen + 1
+            assert seen <= V

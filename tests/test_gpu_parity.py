@@ -9,6 +9,8 @@ the north star's absolute 1e-3 for every model; the randomised-BN stress variant
 bound is scaled by max|logit| / 16 (the unscaled figures are printed and kept in profiles/r2_parity_report.txt).  The emission schedule (which block
 fires on which frame) is integer bookkeeping and must match bit for bit.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -463,6 +465,39 @@ def test_adaptive_kinetics_skeleton_stack(path):
     assert _rel_err(got.cpu(), want) < BLOCK_RTOL, _rel_err(got.cpu(), want)
     if path == "auto":
         assert stack.tensor_core_blocks() == [3, 3]
+
+
+@pytest.mark.skipif(os.environ.get("COSK_TEST_UNVERIFIED") != "1",
+                    reason="k_tc_agcnt has not run on hardware yet (written after the round's GPU budget was spent); off by default")
+@pytest.mark.parametrize("skeleton,V,B", [("ntu", 25, 23), ("ntu", 25, 745), ("kinetics", 18, 23)])
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 128), (128, 256)])
+def test_channel_major_adaptive_graph_conv(monkeypatch, cin, cout, skeleton, V, B):
+    """k_tc_agcnt (adaptive graph conv, dense per-skeleton mix with the channels on the TMEM lanes and the mixing rows broadcast
+    from shared memory): selected for the 128/256-channel adaptive blocks, equal to the step oracle on distinct streams
+    (ragged last tile; B = 745 -> 149 tiles, more than SMs) and to the token-major kernel k_tc_agcn."""
+    blocks = [weights.BlockSpec(cin, cout, 1, True)]
+    arch = ArchSpec(blocks, padding=4, skeleton=skeleton, head=False, block_names=["0."], graph_conv="adaptive")
+    sd = weights.make_state_dict(arch, seed=91 + cin + cout, randomize=True)
+    T = 11
+    x = weights.make_input((B, cin, T, V), seed=92)
+    want = step.StepModel(sd, arch).forward_steps(x)
+    mapped = {}
+    for k, v in sd.items():
+        i, rest = k.split(".", 1)
+        mapped[f"{i}.0.0.{rest}" if rest.startswith("residual") else f"{i}.0.1.{rest}"] = v
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("COSK_AGCN_T", flag)
+        stack = cs.CoStack([cs.BlockSpec(cin, cout, 1, True)], padding=4, skeleton=skeleton, adaptive=True)
+        stack.load_state_dict(mapped, strict=True)
+        out = stack.forward_steps(x.to(DEV))
+        assert stack.device_error() == 0
+        kernel = stack.knobs()["blocks"][0]["gcn"]
+        assert kernel.endswith("k_tc_agcnt" if flag == "1" else "k_tc_agcn"), kernel
+        outs[flag] = out.cpu()
+    assert tuple(outs["1"].shape) == tuple(want.shape)
+    assert _rel_err(outs["1"], want) < BLOCK_RTOL
+    assert _rel_err(outs["1"], outs["0"]) < 2e-5
 
 
 @pytest.mark.parametrize("cls,arch_fn,tag", [

@@ -18,6 +18,18 @@ for total in $TOTALS; do
   fi
   rc=$?
   line=$(grep '^{' gpurun_out/sweep_tmp.log | tail -1)
+  if [ -z "$line" ]; then  # one retry (a failed rendezvous on a fresh box is not a result)
+    cp gpurun_out/sweep_tmp.log gpurun_out/sweep_fail_${G}_${total}.log
+    sleep 3
+    if [ $G -eq 1 ]; then
+      timeout 900 python bench.py --streams $per --steps 40 --warmup 4 --prewarm-s 0.5 --no-cpu-baseline > gpurun_out/sweep_tmp.log 2>&1
+    else
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29651 \
+        bench.py --gpus $G --streams $per --steps 40 --warmup 4 --prewarm-s 0.5 --no-cpu-baseline > gpurun_out/sweep_tmp.log 2>&1
+    fi
+    rc=$?
+    line=$(grep '^{' gpurun_out/sweep_tmp.log | tail -1)
+  fi
   if [ -n "$line" ]; then echo "$line" >> $out; else echo "{\"streams_total\": $total, \"n_gpus\": $G, \"failed\": $rc, \"tail\": \"$(tail -3 gpurun_out/sweep_tmp.log | tr '\n"' ' .' | cut -c1-300)\"}" >> $out; fi
 done
 python - <<PY
