@@ -304,15 +304,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t_pre = time.time()
     # The steps carry a collective (the logit all-gather), so every rank must run the SAME number of them: the decision
-    # to go on is taken by rank-local wall clock and then agreed on (MAX over ranks).  A purely local `while time < limit`
+    # to go on is taken by rank-local wall clock and then agreed on (cs.any_rank: MAX over ranks).  A purely local `while time < limit`
     # lets one rank leave the loop a batch earlier than its peers and meet their all-gather with the barrier's all-reduce.
-    go = torch.zeros(1, device=dev, dtype=torch.int32)
-    while True:
-        go.fill_(1 if time.time() - t_pre < args.prewarm_s else 0)
-        if world > 1:
-            dist.all_reduce(go, op=dist.ReduceOp.MAX)
-        if int(go.item()) == 0:
-            break
+    while cs.any_rank(time.time() - t_pre < args.prewarm_s, dev):
         for _ in range(16):
             step_resident(t)
             t += 1

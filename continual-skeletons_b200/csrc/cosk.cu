@@ -2208,10 +2208,10 @@ int cosk_describe(const cosk_model *m, char *buf, size_t n) {
   char t[1024];
   snprintf(t, sizeof t,
            "\"version\": \"%s\", \"path\": \"%s\", \"pdl\": %d, \"tcn_pair_mask\": %d, \"tcn_reverse\": %d, \"tcn_identity_mma\": %d, "
-           "\"fuse_block\": %d, \"gcn_transposed\": %d, \"agcn_transposed\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
+           "\"fuse_block\": %d, \"gcn_transposed\": %d, \"gcnt_pack\": %d, \"agcn_transposed\": %d, \"gcn_fold_unit\": %d, \"gcn_premix\": %d, \"gcnp_stacked\": %d, \"gcn_identity_mma\": %d, \"merge\": %d, "
            "\"sa_fused\": %d, \"attn_tc\": %d, \"agcn_tc\": %d, \"trace\": %d, ",
            cosk_version(), m->cfg.path == COSK_PATH_AUTO ? "auto" : "simt", m->pdl, m->pair_mask, m->tcn_reverse, m->tcn_identity_mma,
-           m->fuse_block, m->gcn_transposed, m->agcn_transposed, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
+           m->fuse_block, m->gcn_transposed, m->gcnt_pack, m->agcn_transposed, m->gcn_fold_unit, m->gcn_premix, m->gcnp_stacked, m->gcn_identity_mma, m->merge, m->sa_fused, m->attn_tc, m->agcn_tc,
            m->d_trace ? 1 : 0);
   o += t;
   o += "\"blocks\": [";

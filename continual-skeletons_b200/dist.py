@@ -13,6 +13,17 @@ def shard_range(n_streams, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def any_rank(flag, device="cpu", group=None):
+    """True on every rank iff ``flag`` is true on at least one.  For loops whose length is decided by something rank-local
+    (a wall clock, a queue) while their body carries a collective: all ranks must run the same number of iterations, or one
+    of them leaves the loop early and meets its peers' all-gather with a different collective (which deadlocks NCCL)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(int(t.item()))
+
+
 def all_gather_logits(local, n_streams, group=None):
     """local (n_local, classes) -> (n_streams, classes) on every rank, in global stream order."""
     if not (dist.is_available() and dist.is_initialized()):

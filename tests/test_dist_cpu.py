@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from continual_skeletons_b200 import LogitGather, all_gather_logits, shard_range
+from continual_skeletons_b200 import LogitGather, all_gather_logits, any_rank, shard_range
 
 
 def test_shard_range_partitions():
@@ -33,6 +33,14 @@ def _worker(rank, world, port, n_streams, ret):
     for k in (1.0, 2.0):
         g.launch(full[lo:hi] * k)
         ok = ok and bool(torch.equal(g.result(), full * k))
+    # a loop whose length is decided by something rank-local around a body with a collective (bench.py's prewarm): rank 1
+    # wants one more batch than rank 0 -- both must run the same number, or the collectives below would pair up wrongly
+    want, ran = 2 + rank, 0
+    while any_rank(ran < want):
+        t = torch.tensor([float(rank)])
+        dist.all_reduce(t)
+        ran += 1
+    ok = ok and ran == 3 and any_rank(False) is False and any_rank(rank == 1) is True
     ret[rank] = ok
     dist.destroy_process_group()
 
@@ -63,3 +71,7 @@ def test_logit_gather_single_process_passthrough():
     x = torch.rand(3, 4)
     g.launch(x)
     assert g.result() is x
+
+
+def test_any_rank_without_process_group():
+    assert any_rank(True) is True and any_rank(False) is False
