@@ -18,7 +18,9 @@
 #include "tc_kernels.cuh"
 #include "tc_gcnp.cuh"
 #include "tc_gcnt.cuh"
+#ifdef COSK_WITH_AGCNT  // k_tc_agcnt has never run on hardware: compiled in only on request (lib.py: COSK_WITH_AGCNT=1)
 #include "tc_agcnt.cuh"
+#endif
 #include "tc_block.cuh"
 
 using namespace cosk;
@@ -142,9 +144,9 @@ struct cosk_model {
   int gcn_fold_unit = 1;  // k_tc_gcn: fold the gcn_residual branch into W_0 when every self link is exactly 1 (COSK_GCN_FOLD_UNIT=0 disables)
   int gcn_transposed = 1;  // plain graph convs with cout in {128, 256}, cin in {64, 128} on a skeleton tree the kernel is compiled for run on
                            // k_tc_gcnt (channels on the TMEM lanes, adjacency contraction in registers); COSK_GCN_T=0: k_tc_gcn
-  int agcn_transposed = 0;  // adaptive graph convs with cout in {128, 256}, cin in {64, 128}: dense mix on k_tc_agcnt.  OFF: the kernel was
-                            // written after the round's GPU budget was spent -- it compiles (no spills) but has never run on hardware.
-                            // COSK_AGCN_T=1 enables it (tests/test_gpu_parity.py::test_channel_major_adaptive_graph_conv, COSK_TEST_UNVERIFIED=1)
+  int agcn_transposed = 0;  // adaptive graph convs with cout in {128, 256}, cin in {64, 128}: dense mix on k_tc_agcnt.  OFF and not in the
+                            // default build: the kernel was written after the round's GPU budget was spent and has never run on hardware
+                            // (build with COSK_WITH_AGCNT=1, enable with COSK_AGCN_T=1, test with COSK_TEST_UNVERIFIED=1)
   int gcnt_pack = 1;  // k_tc_gcnt: lane pairs trade tokens before the store (32-bit stores of two channels); COSK_GCNT_PACK=0: 16-bit stores
   int fuse_block = 1;  // 64 -> 64 identity-residual blocks: graph conv + temporal conv in one kernel per step (COSK_FUSE_BLOCK=0: two kernels)
   int gcnp_stacked = 1;       // widths (bit 0: 64, bit 1: 128) using the stacked-B product form in k_tc_gcnp
@@ -501,7 +503,12 @@ int prepare(cosk_model *m) {
       }
     }
     b.tc_agcnt = false;
-    if (b.tc_gcn && adaptive && m->agcn_transposed && (bc.cout == 128 || bc.cout == 256) && (bc.cin == 64 || bc.cin == 128) &&
+#ifdef COSK_WITH_AGCNT
+    const bool agcnt_built = true;
+#else
+    const bool agcnt_built = false;
+#endif
+    if (agcnt_built && b.tc_gcn && adaptive && m->agcn_transposed && (bc.cout == 128 || bc.cout == 256) && (bc.cin == 64 || bc.cin == 128) &&
         (V == 25 || V == 18)) {
       // channel-major layout, always four parts: W_0, W_1, W_2, gcn_residual (folded 1x1 conv, or the identity matrix)
       const int P = 4;
@@ -807,12 +814,14 @@ int set_smem_attrs(cosk_model *m) {
   CK(cudaFuncSetAttribute(k_tc_gcnp<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<128, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnp<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcnpCfg<256, false>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_block64, cudaFuncAttributeMaxDynamicSharedMemorySize, TcBlockCfg::kSmemBytes));
+#ifdef COSK_WITH_AGCNT
   CK(cudaFuncSetAttribute(k_tc_agcnt<25, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcnt<25, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcnt<25, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<25, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcnt<18, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcnt<18, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_agcnt<18, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAgcntCfg<18, 2>::kSmemBytes));
+#endif
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 1>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
   CK(cudaFuncSetAttribute(k_tc_gcnt<25, 2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcGcntCfg<25, 2>::kSmemBytes));
@@ -891,6 +900,10 @@ int launch_tc_gcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
 
 // k_tc_agcnt: dense mix of the adaptive graph conv, work items are single tiles
 int launch_tc_agcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
+#ifndef COSK_WITH_AGCNT
+  (void)i, (void)a, (void)s;
+  return fail(m, COSK_ERR_STATE, "k_tc_agcnt is not compiled in (build with -DCOSK_WITH_AGCNT)");
+#else
   const cosk_block_cfg &bc = m->cfg.blocks[i];
   const BlockW &b = m->blk[i];
   TcGcntArgs t;
@@ -914,6 +927,7 @@ int launch_tc_agcnt(cosk_model *m, int i, TcGcnArgs a, cudaStream_t s) {
     else CK(launch_k(m, k_tc_agcnt<18, 2, 256>, grid, block, TcAgcntCfg<18, 2>::kSmemBytes, s, t));
   }
   return COSK_OK;
+#endif
 }
 
 TcGcnpArgs make_gcnp_args(cosk_model *m, int i, const ActBuf &in, int in_slot, int ring_slot) {

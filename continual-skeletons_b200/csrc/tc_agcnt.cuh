@@ -10,8 +10,10 @@
 // per-lane registers, and the operand Y_i[v] of all those FMAs is a register.  One FMA per (partition, v, w, channel) and a
 // quarter of a shared-memory instruction -- against one FMA per loaded shared-memory word in the token-major k_tc_agcn.
 //
-// STATUS: compiles for sm_100a without spills; NOT yet run on hardware (the round's GPU budget was spent before its first launch),
-// so it is off by default (COSK_AGCN_T=1 enables it; parity test gated by COSK_TEST_UNVERIFIED=1).
+// STATUS: compiles for sm_100a without spills; NOT yet run on hardware (the round's GPU budget was spent before its first launch).
+// It is therefore not part of the default build: COSK_WITH_AGCNT=1 (lib.py -> -DCOSK_WITH_AGCNT) compiles it in, COSK_AGCN_T=1
+// selects it at run time, and tests/test_gpu_parity.py::test_channel_major_adaptive_graph_conv (COSK_TEST_UNVERIFIED=1) checks it
+// against the step oracle and the token-major kernel.
 //
 // Work item = (frame, token tile): the tile's mixing rows are one contiguous block of the attention kernel's scratch
 // ([token][3][VP] floats) and arrive with a single bulk copy (double buffered); the X tile stays resident for the item

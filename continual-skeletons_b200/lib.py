@@ -74,6 +74,8 @@ def build_library(force=False, verbose=False):
                 return out
             tmp = f"{out}.{os.getpid()}.tmp"
             cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "cosk.cu")]
+            if os.environ.get("COSK_WITH_AGCNT") == "1":  # the unverified channel-major dense mix (csrc/tc_agcnt.cuh), +2 min
+                cmd.insert(1, "-DCOSK_WITH_AGCNT")
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)
